@@ -1,0 +1,719 @@
+/* oracle/spm_oracle.c -- TEST INFRASTRUCTURE ONLY (see spm_oracle.h).
+ *
+ * Plain-C restatement of the reference's encode hot path, written from the
+ * reference's behaviour, each function citing the file:line it follows
+ * (paths relative to /root/reference).  Data structures are deliberately the
+ * simplest thing that is obviously right (a hashed trie, arrays, a binary heap);
+ * no attempt is made to be fast.
+ *
+ * Parity status: PINNED.  tests/test_oracle_vs_reference.py checks this file
+ *   (a) against the reference's own known-answer vectors for the path
+ *       (src/normalizer_test.cc:37-357, src/unigram_model_test.cc:782-928,
+ *        src/bpe_model_test.cc:49-250, src/sentencepiece_processor_test.cc:186-303,
+ *        src/util_test.cc:127-226) restated as fixtures in tests/golden/kat_*.json,
+ *   (b) against outputs of the reference itself: the UNMODIFIED reference compiled
+ *       into oracle/_ref (ctypes shim oracle/ref_shim.cc) on seeded corpora, and
+ *       the committed golden id dumps under tests/golden/ produced by
+ *       tools/make_golden.py with that same compiled reference.
+ */
+#include "spm_oracle.h"
+
+#include <float.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ------------------------------------------------------------------ utf-8 -- */
+
+/* string_util::OneCharLen, src/util.h:151-153 */
+static inline size_t one_char_len(unsigned char c) {
+  static const unsigned char T[16] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 2, 2, 3, 4};
+  return T[c >> 4];
+}
+/* IsTrailByte, src/util.h:157 */
+static inline int is_trail(unsigned char c) { return (c & 0xC0) == 0x80; }
+/* IsValidCodepoint, src/util.h:159-161 */
+static inline int valid_cp(uint32_t c) { return c < 0xD800 || (c >= 0xE000 && c <= 0x10FFFF); }
+
+/* string_util::DecodeUTF8, src/util.cc:51-84.  Returns the code point or
+ * 0xFFFD (kUnicodeError) with *mblen = 1 for malformed input. */
+static uint32_t decode_utf8(const unsigned char *b, size_t len, size_t *mblen) {
+  if (b[0] < 0x80) { *mblen = 1; return b[0]; }
+  if (len >= 2 && (b[0] & 0xE0) == 0xC0) {
+    const uint32_t cp = ((uint32_t)(b[0] & 0x1F) << 6) | (b[1] & 0x3F);
+    if (is_trail(b[1]) && cp >= 0x80 && valid_cp(cp)) { *mblen = 2; return cp; }
+  } else if (len >= 3 && (b[0] & 0xF0) == 0xE0) {
+    const uint32_t cp = ((uint32_t)(b[0] & 0x0F) << 12) | ((uint32_t)(b[1] & 0x3F) << 6) | (b[2] & 0x3F);
+    if (is_trail(b[1]) && is_trail(b[2]) && cp >= 0x800 && valid_cp(cp)) { *mblen = 3; return cp; }
+  } else if (len >= 4 && (b[0] & 0xF8) == 0xF0) {
+    const uint32_t cp = ((uint32_t)(b[0] & 0x07) << 18) | ((uint32_t)(b[1] & 0x3F) << 12) |
+                        ((uint32_t)(b[2] & 0x3F) << 6) | (b[3] & 0x3F);
+    if (is_trail(b[1]) && is_trail(b[2]) && is_trail(b[3]) && cp >= 0x10000 && valid_cp(cp)) {
+      *mblen = 4;
+      return cp;
+    }
+  }
+  *mblen = 1;
+  return 0xFFFD;
+}
+/* IsValidDecodeUTF8, src/util.h:173-176: a literal U+FFFD (3 bytes) is valid */
+static int is_valid_decode_utf8(const unsigned char *b, size_t len, size_t *mblen) {
+  const uint32_t c = decode_utf8(b, len, mblen);
+  return c != 0xFFFD || *mblen == 3;
+}
+
+/* ------------------------------------------------------------ hashed trie -- */
+
+typedef struct {
+  uint32_t *keys;   /* ((node << 8) | label) + 1 ; 0 = empty */
+  int32_t *child;
+  uint32_t cap;     /* power of two */
+  uint32_t used;
+  int32_t *value;   /* per node: key value or -1 */
+  uint32_t n_nodes, node_cap;
+} htrie;
+
+static void ht_init(htrie *t) {
+  memset(t, 0, sizeof *t);
+  t->cap = 1024;
+  t->keys = calloc(t->cap, sizeof(uint32_t));
+  t->child = malloc(t->cap * sizeof(int32_t));
+  t->node_cap = 1024;
+  t->value = malloc(t->node_cap * sizeof(int32_t));
+  t->value[0] = -1;
+  t->n_nodes = 1;
+}
+static void ht_free(htrie *t) { free(t->keys); free(t->child); free(t->value); }
+static inline uint32_t ht_hash(uint32_t k) { k *= 0x9E3779B1u; return k ^ (k >> 15); }
+static int32_t ht_child(const htrie *t, uint32_t node, unsigned char label) {
+  const uint32_t k = ((node << 8) | label) + 1;
+  uint32_t h = ht_hash(k) & (t->cap - 1);
+  while (t->keys[h]) {
+    if (t->keys[h] == k) return t->child[h];
+    h = (h + 1) & (t->cap - 1);
+  }
+  return -1;
+}
+static void ht_put(htrie *t, uint32_t k, int32_t c) {
+  uint32_t h = ht_hash(k) & (t->cap - 1);
+  while (t->keys[h]) h = (h + 1) & (t->cap - 1);
+  t->keys[h] = k;
+  t->child[h] = c;
+  t->used++;
+}
+static void ht_grow(htrie *t) {
+  uint32_t *ok = t->keys;
+  int32_t *oc = t->child;
+  const uint32_t ocap = t->cap;
+  t->cap *= 2;
+  t->keys = calloc(t->cap, sizeof(uint32_t));
+  t->child = malloc(t->cap * sizeof(int32_t));
+  t->used = 0;
+  for (uint32_t i = 0; i < ocap; ++i) if (ok[i]) ht_put(t, ok[i], oc[i]);
+  free(ok); free(oc);
+}
+/* returns 0 if inserted, 1 if the key already existed */
+static int ht_insert(htrie *t, const char *s, size_t len, int32_t value) {
+  uint32_t node = 0;
+  for (size_t i = 0; i < len; ++i) {
+    int32_t c = ht_child(t, node, (unsigned char)s[i]);
+    if (c < 0) {
+      if (t->used * 2 >= t->cap) ht_grow(t);
+      if (t->n_nodes == t->node_cap) {
+        t->node_cap *= 2;
+        t->value = realloc(t->value, t->node_cap * sizeof(int32_t));
+      }
+      c = (int32_t)t->n_nodes++;
+      t->value[c] = -1;
+      ht_put(t, ((node << 8) | (unsigned char)s[i]) + 1, c);
+    }
+    node = (uint32_t)c;
+  }
+  if (t->value[node] >= 0) return 1;
+  t->value[node] = value;
+  return 0;
+}
+static int32_t ht_exact(const htrie *t, const char *s, size_t len) {
+  uint32_t node = 0;
+  for (size_t i = 0; i < len; ++i) {
+    const int32_t c = ht_child(t, node, (unsigned char)s[i]);
+    if (c < 0) return -1;
+    node = (uint32_t)c;
+  }
+  return t->value[node];
+}
+
+/* ------------------------------------------------------------------ model -- */
+
+struct oracle_model {
+  int32_t model_type, vocab_size;
+  char *piece_bytes;
+  uint32_t *piece_off;
+  float *scores;
+  uint8_t *types;
+  uint8_t byte_fallback, add_dummy_prefix, remove_extra_whitespaces, escape_whitespaces,
+      treat_whitespace_as_suffix;
+  /* ModelInterface::InitializePieces, src/model_interface.cc:63-151 */
+  htrie pieces;    /* pieces_: NORMAL | USER_DEFINED | UNUSED -> id */
+  htrie reserved;  /* reserved_id_map_: CONTROL | UNKNOWN | BYTE -> id */
+  htrie user;      /* PrefixMatcher over USER_DEFINED, src/normalizer.cc:311-322 */
+  int has_user;
+  int32_t unk_id;
+  float min_score, max_score;
+  int32_t byte_to_id[256];
+  /* precompiled charsmap, src/normalizer.cc:274-309 */
+  uint8_t *charsmap;
+  const uint32_t *cm_units;
+  size_t cm_nunits;
+  const char *cm_targets;
+  size_t cm_targets_len;
+};
+
+void oracle_free(void *p) { free(p); }
+float oracle_min_score(const oracle_model *m) { return m->min_score; }
+float oracle_max_score(const oracle_model *m) { return m->max_score; }
+int32_t oracle_unk_id(const oracle_model *m) { return m->unk_id; }
+
+/* ModelInterface::PieceToId, src/model_interface.cc:51-61 */
+static int32_t piece_to_id(const oracle_model *m, const char *s, size_t len) {
+  int32_t id = ht_exact(&m->reserved, s, len);
+  if (id >= 0) return id;
+  id = ht_exact(&m->pieces, s, len);
+  if (id >= 0) return id;
+  return m->unk_id;
+}
+
+static void set_err(char *err, size_t errlen, const char *msg) {
+  if (err && errlen) snprintf(err, errlen, "%s", msg);
+}
+
+oracle_model *oracle_create(const oracle_model_desc *d, char *err, size_t errlen) {
+  oracle_model *m = calloc(1, sizeof *m);
+  m->model_type = d->model_type;
+  m->vocab_size = d->vocab_size;
+  const uint32_t total = d->piece_off[d->vocab_size];
+  m->piece_bytes = malloc(total + 1);
+  memcpy(m->piece_bytes, d->piece_bytes, total);
+  m->piece_off = malloc(sizeof(uint32_t) * (size_t)(d->vocab_size + 1));
+  memcpy(m->piece_off, d->piece_off, sizeof(uint32_t) * (size_t)(d->vocab_size + 1));
+  m->scores = malloc(sizeof(float) * (size_t)d->vocab_size);
+  memcpy(m->scores, d->scores, sizeof(float) * (size_t)d->vocab_size);
+  m->types = malloc((size_t)d->vocab_size);
+  memcpy(m->types, d->types, (size_t)d->vocab_size);
+  m->byte_fallback = d->byte_fallback;
+  m->add_dummy_prefix = d->add_dummy_prefix;
+  m->remove_extra_whitespaces = d->remove_extra_whitespaces;
+  m->escape_whitespaces = d->escape_whitespaces;
+  m->treat_whitespace_as_suffix = d->treat_whitespace_as_suffix;
+  ht_init(&m->pieces);
+  ht_init(&m->reserved);
+  ht_init(&m->user);
+  m->unk_id = -1;
+  int byte_found[256] = {0};
+  /* src/model_interface.cc:88-133 */
+  for (int32_t i = 0; i < d->vocab_size; ++i) {
+    const char *p = m->piece_bytes + m->piece_off[i];
+    const size_t l = m->piece_off[i + 1] - m->piece_off[i];
+    const uint8_t t = m->types[i];
+    if (l == 0) { set_err(err, errlen, "piece must not be empty."); goto fail; }
+    const int normal = (t == ORACLE_NORMAL || t == ORACLE_USER_DEFINED || t == ORACLE_UNUSED);
+    if (ht_insert(normal ? &m->pieces : &m->reserved, p, l, i)) {
+      set_err(err, errlen, "piece is already defined.");
+      goto fail;
+    }
+    if (t == ORACLE_USER_DEFINED) { ht_insert(&m->user, p, l, i); m->has_user = 1; }
+    if (t == ORACLE_UNKNOWN) {
+      if (m->unk_id >= 0) { set_err(err, errlen, "unk is already defined."); goto fail; }
+      m->unk_id = i;
+    }
+    if (t == ORACLE_BYTE) {
+      if (!m->byte_fallback) { set_err(err, errlen, "byte piece found although byte_fallback is false."); goto fail; }
+      unsigned v;
+      char tail;
+      /* PieceToByte: exact "<0x%02X>" form, src/model_interface.cc:210-229 */
+      if (l == 6 && sscanf(p, "<0x%02X%c", &v, &tail) == 2 && tail == '>' && v < 256) {
+        char canon[8];
+        snprintf(canon, sizeof canon, "<0x%02X>", v);
+        if (memcmp(canon, p, 6) != 0) { set_err(err, errlen, "byte piece is invalid."); goto fail; }
+        byte_found[v] = 1;
+      } else { set_err(err, errlen, "byte piece is invalid."); goto fail; }
+    }
+  }
+  if (m->unk_id < 0) { set_err(err, errlen, "unk is not defined."); goto fail; }
+  if (m->byte_fallback)
+    for (int b = 0; b < 256; ++b)
+      if (!byte_found[b]) { set_err(err, errlen, "there are not 256 byte pieces although byte_fallback is true."); goto fail; }
+  /* unigram::Model ctor, src/unigram_model.cc:657-664 (NB: max starts at FLT_MIN) */
+  m->min_score = FLT_MAX;
+  m->max_score = FLT_MIN;
+  for (int32_t i = 0; i < d->vocab_size; ++i)
+    if (m->types[i] == ORACLE_NORMAL) {
+      if (m->scores[i] < m->min_score) m->min_score = m->scores[i];
+      if (m->scores[i] > m->max_score) m->max_score = m->scores[i];
+    }
+  /* PieceToId(ByteToPiece(b)), src/sentencepiece_processor.cc:587-588 */
+  for (int b = 0; b < 256; ++b) {
+    char bp[8];
+    snprintf(bp, sizeof bp, "<0x%02X>", b);
+    m->byte_to_id[b] = piece_to_id(m, bp, 6);
+  }
+  /* Normalizer::Init / DecodePrecompiledCharsMap, src/normalizer.cc:47-69,274-309 */
+  if (d->charsmap_len) {
+    uint32_t trie_bytes = 0;
+    if (d->charsmap_len <= 4) { set_err(err, errlen, "Blob for normalization rule is broken."); goto fail; }
+    memcpy(&trie_bytes, d->charsmap, 4);
+    if (trie_bytes >= d->charsmap_len) { set_err(err, errlen, "Trie data size exceeds the input blob size."); goto fail; }
+    /* keep a 4-byte-aligned private copy */
+    m->charsmap = malloc(d->charsmap_len + 8);
+    memcpy(m->charsmap, d->charsmap, d->charsmap_len);
+    m->charsmap[d->charsmap_len] = 0;
+    m->cm_units = (const uint32_t *)(m->charsmap + 4);
+    m->cm_nunits = trie_bytes / 4;
+    m->cm_targets = (const char *)m->charsmap + 4 + trie_bytes;
+    m->cm_targets_len = d->charsmap_len - 4 - trie_bytes;
+  }
+  return m;
+fail:
+  oracle_destroy(m);
+  return NULL;
+}
+
+void oracle_destroy(oracle_model *m) {
+  if (!m) return;
+  ht_free(&m->pieces); ht_free(&m->reserved); ht_free(&m->user);
+  free(m->piece_bytes); free(m->piece_off); free(m->scores); free(m->types); free(m->charsmap);
+  free(m);
+}
+
+void oracle_set_types(oracle_model *m, const uint8_t *types) {
+  memcpy(m->types, types, (size_t)m->vocab_size);
+}
+
+/* ------------------------------------------------------ darts (charsmap) -- */
+
+/* Darts::DoubleArrayUnit, third_party/darts_clone/darts.h:50-80 */
+static inline uint32_t da_offset(uint32_t u) { return (u >> 10) << ((u & (1u << 9)) >> 6); }
+static inline uint32_t da_label(uint32_t u) { return u & ((1u << 31) | 0xFF); }
+static inline int da_has_leaf(uint32_t u) { return (u >> 8) & 1; }
+static inline uint32_t da_value(uint32_t u) { return u & ((1u << 31) - 1); }
+
+/* Longest match of commonPrefixSearch (darts.h:469-513) as used by
+ * NormalizePrefix (normalizer.cc:215-228): returns the longest key length (0 if
+ * none) and its value. */
+static size_t charsmap_longest(const oracle_model *m, const unsigned char *key, size_t len, uint32_t *value) {
+  if (!m->cm_units) return 0;
+  size_t longest = 0;
+  uint32_t node = 0;
+  uint32_t unit = m->cm_units[node];
+  node ^= da_offset(unit);
+  for (size_t i = 0; i < len; ++i) {
+    node ^= key[i];
+    if (node >= m->cm_nunits) break; /* the reference would read out of bounds; blobs are well formed */
+    unit = m->cm_units[node];
+    if (da_label(unit) != key[i]) break;
+    node ^= da_offset(unit);
+    if (da_has_leaf(unit)) {
+      longest = i + 1; /* results come in increasing length; the last one wins (normalizer.cc:223-228) */
+      *value = da_value(m->cm_units[node]);
+    }
+  }
+  return longest;
+}
+
+/* PrefixMatcher::PrefixMatch, src/normalizer.cc:324-346 */
+static size_t prefix_match(const oracle_model *m, const unsigned char *w, size_t len, int *found) {
+  size_t mblen = 0;
+  *found = 0;
+  if (m->has_user) {
+    uint32_t node = 0;
+    for (size_t i = 0; i < len; ++i) {
+      const int32_t c = ht_child(&m->user, node, w[i]);
+      if (c < 0) break;
+      node = (uint32_t)c;
+      if (m->user.value[node] >= 0) { mblen = i + 1; *found = 1; }
+    }
+  }
+  if (!*found) {
+    const size_t l = one_char_len(w[0]);
+    mblen = len < l ? len : l;
+  }
+  return mblen;
+}
+
+/* --------------------------------------------------------------- normalize -- */
+
+typedef struct { char *s; uint64_t *map; size_t n, cap; } nbuf;
+static void nb_push(nbuf *b, char c, uint64_t consumed) {
+  if (b->n == b->cap) {
+    b->cap = b->cap ? b->cap * 2 : 256;
+    b->s = realloc(b->s, b->cap + 1);
+    b->map = realloc(b->map, sizeof(uint64_t) * (b->cap + 2));
+  }
+  b->s[b->n] = c;
+  b->map[b->n] = consumed;
+  b->n++;
+}
+
+/* Normalizer::NormalizePrefix, src/normalizer.cc:195-253.  Returns the consumed
+ * byte count; *sp / *sp_len is the replacement string. */
+static size_t normalize_prefix(const oracle_model *m, const unsigned char *in, size_t len, const char **sp,
+                               size_t *sp_len) {
+  int found = 0;
+  const size_t ml = prefix_match(m, in, len, &found);
+  if (found) { *sp = (const char *)in; *sp_len = ml; return ml; }
+  uint32_t value = 0;
+  const size_t longest = charsmap_longest(m, in, len, &value);
+  if (longest == 0) {
+    size_t l = 0;
+    if (!is_valid_decode_utf8(in, len, &l)) {
+      *sp = "\xEF\xBF\xBD"; *sp_len = 3; return 1;
+    }
+    *sp = (const char *)in; *sp_len = l; return l;
+  }
+  *sp = m->cm_targets + value;
+  *sp_len = strlen(*sp); /* NUL-delimited, normalizer.cc:247-249 */
+  return longest;
+}
+
+static void add_ws(const oracle_model *m, nbuf *b, uint64_t consumed) {
+  if (m->escape_whitespaces) {
+    nb_push(b, (char)0xE2, consumed); nb_push(b, (char)0x96, consumed); nb_push(b, (char)0x81, consumed);
+  } else {
+    nb_push(b, ' ', consumed);
+  }
+}
+
+int oracle_normalize(const oracle_model *m, const char *in_, size_t len, char **out, size_t *out_len,
+                     uint64_t **n2o, size_t *n2o_len) {
+  const unsigned char *in = (const unsigned char *)in_;
+  nbuf b = {0};
+  *out = NULL; *out_len = 0; *n2o = NULL; *n2o_len = 0;
+  if (len == 0) return 0;
+  uint64_t consumed = 0;
+  const char *sp; size_t spl;
+  /* heading spaces, normalizer.cc:86-95 */
+  if (m->remove_extra_whitespaces) {
+    while (len) {
+      const size_t c = normalize_prefix(m, in, len, &sp, &spl);
+      if (!(spl == 1 && sp[0] == ' ')) break;
+      in += c; len -= c; consumed += c;
+    }
+  }
+  if (len == 0) return 0;
+  if (!m->treat_whitespace_as_suffix && m->add_dummy_prefix) add_ws(m, &b, consumed);
+  int is_prev_space = m->remove_extra_whitespaces;
+  while (len) {
+    const size_t c = normalize_prefix(m, in, len, &sp, &spl);
+    while (is_prev_space && spl && sp[0] == ' ') { ++sp; --spl; }
+    if (spl) {
+      for (size_t n = 0; n < spl; ++n) {
+        if (m->escape_whitespaces && sp[n] == ' ') {
+          nb_push(&b, (char)0xE2, consumed); nb_push(&b, (char)0x96, consumed); nb_push(&b, (char)0x81, consumed);
+        } else {
+          nb_push(&b, sp[n], consumed);
+        }
+      }
+      is_prev_space = sp[spl - 1] == ' ';
+    }
+    consumed += c; in += c; len -= c;
+    if (!m->remove_extra_whitespaces) is_prev_space = 0;
+  }
+  /* trailing spaces, normalizer.cc:166-176 */
+  if (m->remove_extra_whitespaces) {
+    const char *space = m->escape_whitespaces ? "\xE2\x96\x81" : " ";
+    const size_t sl = m->escape_whitespaces ? 3 : 1;
+    while (b.n >= sl && memcmp(b.s + b.n - sl, space, sl) == 0) {
+      const size_t length = b.n - sl;
+      consumed = b.map[length];
+      b.n = length;
+    }
+  }
+  if (m->treat_whitespace_as_suffix && m->add_dummy_prefix) add_ws(m, &b, consumed);
+  if (b.n == 0 && b.s == NULL) { /* nothing was ever pushed */
+    b.s = malloc(1); b.map = malloc(sizeof(uint64_t) * 2);
+  }
+  b.map[b.n] = consumed; /* normalizer.cc:181 (capacity reserved by nb_push) */
+  *out = b.s; *out_len = b.n; *n2o = b.map; *n2o_len = b.n + 1;
+  return 0;
+}
+
+/* ------------------------------------------------------------------ unigram -- */
+
+typedef struct { int32_t id; float best_path_score; int32_t starts_at; } best_node;
+
+/* unigram::Model::EncodeOptimized, src/unigram_model.cc:889-1020 */
+static int unigram_encode(const oracle_model *m, const unsigned char *norm, size_t size, int32_t **ids_out,
+                          uint32_t **ends_out, size_t *n_out) {
+  *ids_out = NULL; *ends_out = NULL; *n_out = 0;
+  if (size == 0) return 0;
+  const float unk_score = m->min_score - 10.0f; /* kUnkPenalty, unigram_model.cc:955 */
+  best_node *best = malloc(sizeof(best_node) * (size + 1));
+  for (size_t i = 0; i <= size; ++i) { best[i].id = -1; best[i].best_path_score = 0; best[i].starts_at = -1; }
+  size_t starts_at = 0;
+  while (starts_at < size) {
+    uint32_t node = 0;
+    size_t key_pos = starts_at;
+    const float till_here = best[starts_at].best_path_score;
+    int has_single_node = 0;
+    size_t mblen = one_char_len(norm[starts_at]);
+    if (mblen > size - starts_at) mblen = size - starts_at;
+    while (key_pos < size) {
+      const int32_t c = ht_child(&m->pieces, node, norm[key_pos]);
+      if (c < 0) break;               /* traverse() == -2 */
+      node = (uint32_t)c;
+      ++key_pos;
+      const int32_t ret = m->pieces.value[node];
+      if (ret < 0) continue;          /* traverse() == -1 */
+      if (m->types[ret] == ORACLE_UNUSED) continue;
+      best_node *t = &best[key_pos];
+      const size_t length = key_pos - starts_at;
+      /* Q1: `score` has type double (common type of double and float), the
+       * candidate is double, the comparison is double > (double)float and the
+       * store truncates to float.  unigram_model.cc:979-989 */
+      const double score = m->types[ret] == ORACLE_USER_DEFINED
+                               ? ((double)((float)length * m->max_score) - 0.1)
+                               : (double)m->scores[ret];
+      const double cand = score + (double)till_here;
+      if (t->starts_at == -1 || cand > (double)t->best_path_score) {
+        t->best_path_score = (float)cand;
+        t->starts_at = (int32_t)starts_at;
+        t->id = ret;
+      }
+      if (!has_single_node && length == mblen) has_single_node = 1;
+    }
+    if (!has_single_node) {
+      best_node *t = &best[starts_at + mblen];
+      const float cand = unk_score + till_here; /* float + float, unigram_model.cc:997-998 */
+      if (t->starts_at == -1 || cand > t->best_path_score) {
+        t->best_path_score = cand;
+        t->starts_at = (int32_t)starts_at;
+        t->id = m->unk_id;
+      }
+    }
+    starts_at += mblen;
+  }
+  /* backtrack, unigram_model.cc:1010-1018 */
+  size_t cnt = 0;
+  for (size_t e = size; e > 0; e = (size_t)best[e].starts_at) ++cnt;
+  int32_t *ids = malloc(sizeof(int32_t) * (cnt ? cnt : 1));
+  uint32_t *ends = malloc(sizeof(uint32_t) * (cnt ? cnt : 1));
+  size_t k = cnt;
+  for (size_t e = size; e > 0; e = (size_t)best[e].starts_at) {
+    --k;
+    ids[k] = best[e].id;
+    ends[k] = (uint32_t)e;
+  }
+  free(best);
+  *ids_out = ids; *ends_out = ends; *n_out = cnt;
+  return 0;
+}
+
+/* ---------------------------------------------------------------------- bpe -- */
+
+typedef struct { int32_t left, right; float score; size_t size; } sym_pair;
+typedef struct { int32_t prev, next; int freeze; size_t off, len; } symbol;
+typedef struct { sym_pair *a; size_t n, cap; } agenda_t;
+
+/* SymbolPairComparator, src/bpe_model.cc:51-57: "less" for a max-heap */
+static inline int pair_less(const sym_pair *h1, const sym_pair *h2) {
+  return h1->score < h2->score || (h1->score == h2->score && h1->left > h2->left);
+}
+static void agenda_push(agenda_t *q, sym_pair p) {
+  if (q->n == q->cap) { q->cap = q->cap ? q->cap * 2 : 256; q->a = realloc(q->a, q->cap * sizeof(sym_pair)); }
+  size_t i = q->n++;
+  q->a[i] = p;
+  while (i > 0) {
+    const size_t parent = (i - 1) / 2;
+    if (!pair_less(&q->a[parent], &q->a[i])) break;
+    sym_pair t = q->a[parent]; q->a[parent] = q->a[i]; q->a[i] = t;
+    i = parent;
+  }
+}
+static sym_pair agenda_pop(agenda_t *q) {
+  sym_pair top = q->a[0];
+  q->a[0] = q->a[--q->n];
+  size_t i = 0;
+  for (;;) {
+    size_t l = 2 * i + 1, r = l + 1, b = i;
+    if (l < q->n && pair_less(&q->a[b], &q->a[l])) b = l;
+    if (r < q->n && pair_less(&q->a[b], &q->a[r])) b = r;
+    if (b == i) break;
+    sym_pair t = q->a[b]; q->a[b] = q->a[i]; q->a[i] = t;
+    i = b;
+  }
+  return top;
+}
+
+/* rev_merge, src/bpe_model.cc:72-76,102-106: keyed by the merged string's
+ * CONTENT; a later insertion with the same content overwrites. */
+typedef struct { size_t off, len, loff, llen, roff, rlen; } revm;
+typedef struct { revm *a; size_t n, cap; } revm_tab;
+
+static void revm_set(revm_tab *t, const unsigned char *base, revm e) {
+  for (size_t i = 0; i < t->n; ++i)
+    if (t->a[i].len == e.len && memcmp(base + t->a[i].off, base + e.off, e.len) == 0) { t->a[i] = e; return; }
+  if (t->n == t->cap) { t->cap = t->cap ? t->cap * 2 : 16; t->a = realloc(t->a, t->cap * sizeof(revm)); }
+  t->a[t->n++] = e;
+}
+static const revm *revm_find(const revm_tab *t, const unsigned char *base, size_t off, size_t len) {
+  for (size_t i = 0; i < t->n; ++i)
+    if (t->a[i].len == len && memcmp(base + t->a[i].off, base + off, len) == 0) return &t->a[i];
+  return NULL;
+}
+
+typedef struct { int32_t *ids; uint32_t *ends; size_t n, cap; } outv;
+static void out_push(outv *o, int32_t id, uint32_t end) {
+  if (o->n == o->cap) {
+    o->cap = o->cap ? o->cap * 2 : 64;
+    o->ids = realloc(o->ids, o->cap * sizeof(int32_t));
+    o->ends = realloc(o->ends, o->cap * sizeof(uint32_t));
+  }
+  o->ids[o->n] = id; o->ends[o->n] = end; o->n++;
+}
+
+/* resegment, src/bpe_model.cc:175-193 */
+static void resegment(const oracle_model *m, const unsigned char *base, const revm_tab *rm, size_t off, size_t len,
+                      outv *o) {
+  const int32_t id = piece_to_id(m, (const char *)base + off, len);
+  if (id == -1 || m->types[id] != ORACLE_UNUSED) { out_push(o, id, (uint32_t)(off + len)); return; }
+  const revm *p = revm_find(rm, base, off, len);
+  if (!p) { out_push(o, id, (uint32_t)(off + len)); return; }
+  /* NB: the reference recurses on the string_views recorded in rev_merge, which
+   * may point at ANOTHER occurrence of the same content; only the content
+   * matters for ids, but the piece boundaries are taken relative to the current
+   * occurrence here (lengths are what PopulateSentencePieceText consumes). */
+  resegment(m, base, rm, off, p->llen, o);
+  resegment(m, base, rm, off + p->llen, p->rlen, o);
+}
+
+/* bpe::Model::SampleEncode with alpha = 0, src/bpe_model.cc:38-203 */
+static int bpe_encode(const oracle_model *m, const unsigned char *norm, size_t size, int32_t **ids_out,
+                      uint32_t **ends_out, size_t *n_out) {
+  *ids_out = NULL; *ends_out = NULL; *n_out = 0;
+  if (size == 0) return 0;
+  symbol *sym = malloc(sizeof(symbol) * size);
+  size_t nsym = 0;
+  /* split into characters; user-defined symbols are frozen, bpe_model.cc:110-120 */
+  {
+    size_t pos = 0;
+    while (pos < size) {
+      int found = 0;
+      const size_t mblen = prefix_match(m, norm + pos, size - pos, &found);
+      symbol s;
+      s.freeze = found;
+      s.off = pos; s.len = mblen;
+      s.prev = nsym == 0 ? -1 : (int32_t)nsym - 1;
+      pos += mblen;
+      s.next = pos >= size ? -1 : (int32_t)nsym + 1;
+      sym[nsym++] = s;
+    }
+  }
+  agenda_t q = {0};
+  revm_tab rm = {0};
+#define MAYBE_ADD(L, R)                                                                       \
+  do {                                                                                        \
+    const int32_t l_ = (L), r_ = (R);                                                         \
+    if (l_ == -1 || r_ == -1 || sym[l_].freeze || sym[r_].freeze) break;                      \
+    const size_t plen = sym[l_].len + sym[r_].len;                                            \
+    const int32_t pid = ht_exact(&m->pieces, (const char *)norm + sym[l_].off, plen);         \
+    if (pid < 0) break;                                                                       \
+    sym_pair h = {l_, r_, m->scores[pid], plen};                                              \
+    agenda_push(&q, h);                                                                       \
+    if (m->types[pid] == ORACLE_UNUSED) {                                                     \
+      revm e = {sym[l_].off, plen, sym[l_].off, sym[l_].len, sym[r_].off, sym[r_].len};       \
+      revm_set(&rm, norm, e);                                                                 \
+    }                                                                                         \
+  } while (0)
+  for (size_t i = 1; i < nsym; ++i) MAYBE_ADD((int32_t)i - 1, (int32_t)i);
+  while (q.n) {
+    const sym_pair top = agenda_pop(&q);
+    /* stale entry check, bpe_model.cc:147-151 */
+    if (sym[top.left].len == 0 || sym[top.right].len == 0 ||
+        sym[top.left].len + sym[top.right].len != top.size)
+      continue;
+    sym[top.left].len += sym[top.right].len;
+    sym[top.left].next = sym[top.right].next;
+    if (sym[top.right].next >= 0) sym[sym[top.right].next].prev = top.left;
+    sym[top.right].len = 0;
+    MAYBE_ADD(sym[top.left].prev, top.left);
+    MAYBE_ADD(top.left, sym[top.left].next);
+  }
+#undef MAYBE_ADD
+  outv o = {0};
+  for (int32_t i = 0; i != -1; i = sym[i].next) resegment(m, norm, &rm, sym[i].off, sym[i].len, &o);
+  free(sym); free(q.a); free(rm.a);
+  *ids_out = o.ids; *ends_out = o.ends; *n_out = o.n;
+  return 0;
+}
+
+int oracle_model_encode(const oracle_model *m, const char *norm, size_t len, int32_t **ids, uint32_t **ends,
+                        size_t *n) {
+  if (m->model_type == ORACLE_UNIGRAM) return unigram_encode(m, (const unsigned char *)norm, len, ids, ends, n);
+  if (m->model_type == ORACLE_BPE) return bpe_encode(m, (const unsigned char *)norm, len, ids, ends, n);
+  return 2;
+}
+
+/* ----------------------------------------------------- processor: id path -- */
+
+/* SentencePieceProcessor::Encode + PopulateSentencePieceText id path,
+ * src/sentencepiece_processor.cc:547-651 */
+int oracle_encode(const oracle_model *m, const char *in, size_t len, int32_t **ids_out, uint32_t **tok_end_out,
+                  size_t *n_out) {
+  char *norm; size_t nlen; uint64_t *n2o; size_t n2o_len;
+  *ids_out = NULL; *tok_end_out = NULL; *n_out = 0;
+  if (oracle_normalize(m, in, len, &norm, &nlen, &n2o, &n2o_len)) return 1;
+  int32_t *ids; uint32_t *ends; size_t n;
+  int rc = oracle_model_encode(m, norm ? norm : "", nlen, &ids, &ends, &n);
+  if (rc) { free(norm); free(n2o); return rc; }
+  outv o = {0};
+  size_t consumed = 0;
+  int is_prev_unk = 0;
+  for (size_t k = 0; k < n; ++k) {
+    const int32_t id = ids[k];
+    const size_t wlen = ends[k] - (k ? ends[k - 1] : 0);
+    if (wlen == 0) { rc = 3; break; } /* "Empty piece is not allowed." :557 */
+    const int is_unk = (id == m->unk_id);                    /* IsUnknown, model_interface.h:207-210 */
+    const int is_ctrl = id >= 0 && m->types[id] == ORACLE_CONTROL;
+    if (is_ctrl) {
+      /* zero-width control piece: `consumed` does not advance (:561-567); the
+       * final consumed == size check then fails.  Encoders never emit these. */
+      rc = 4;
+      break;
+    }
+    if (is_unk && m->byte_fallback) {
+      for (size_t i = 0; i < wlen; ++i)  /* one <0xXX> piece per byte, :581-603 */
+        out_push(&o, m->byte_to_id[(unsigned char)norm[consumed + i]], (uint32_t)(consumed + i + 1));
+    } else if (is_prev_unk && is_unk) {
+      o.ends[o.n - 1] = (uint32_t)(consumed + wlen);         /* merge unk run, :609-613 */
+    } else {
+      out_push(&o, id, (uint32_t)(consumed + wlen));
+    }
+    consumed += wlen;
+    is_prev_unk = is_unk;
+  }
+  if (!rc && consumed != nlen) rc = 5; /* "all normalized characters are not consumed." :628 */
+  free(ids); free(ends); free(norm); free(n2o);
+  if (rc) { free(o.ids); free(o.ends); return rc; }
+  *ids_out = o.ids; *tok_end_out = o.ends; *n_out = o.n;
+  return 0;
+}
+
+int oracle_encode_batch(const oracle_model *m, const char *bytes, const uint64_t *offs, size_t n, int32_t **ids_out,
+                        uint64_t *id_offsets) {
+  size_t cap = 1024, total = 0;
+  int32_t *all = malloc(cap * sizeof(int32_t));
+  for (size_t i = 0; i < n; ++i) {
+    int32_t *ids; uint32_t *te; size_t k;
+    const int rc = oracle_encode(m, bytes + offs[i], (size_t)(offs[i + 1] - offs[i]), &ids, &te, &k);
+    if (rc) { free(all); return (int)(i + 1); }
+    id_offsets[i] = total;
+    if (total + k > cap) { while (total + k > cap) cap *= 2; all = realloc(all, cap * sizeof(int32_t)); }
+    if (k) memcpy(all + total, ids, k * sizeof(int32_t));
+    total += k;
+    free(ids); free(te);
+  }
+  id_offsets[n] = total;
+  *ids_out = all;
+  return 0;
+}
