@@ -1,0 +1,915 @@
+// engine.cu -- host side of the engine and the extern "C" boundary (include/spm_b200.h).
+//
+// Mirrors what SentencePieceProcessor::Load builds on the CPU
+// (src/sentencepiece_processor.cc:242-281; ModelInterface::InitializePieces
+// src/model_interface.cc:63-151; unigram::Model ctor src/unigram_model.cc:652-670;
+// Normalizer::Init src/normalizer.cc:47-69) as flat device tables, and drives the
+// kernels of kernels.cuh / bpe_kernel.cuh for a packed batch of sentences.
+//
+// There is no CPU fallback anywhere in this file: without a CUDA device
+// spm_engine_create fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/spm_b200.h"
+#include "bpe_kernel.cuh"
+#include "device_model.h"
+#include "kernels.cuh"
+#include "model_reader.h"
+#include "trie_builder.h"
+
+using namespace spm_b200;
+
+namespace {
+
+std::string g_create_error;
+std::mutex g_create_mu;
+
+#define CUDA_TRY(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t err__ = (expr);                                                                 \
+    if (err__ != cudaSuccess) {                                                                 \
+      set_error(std::string(#expr) + ": " + cudaGetErrorString(err__));                         \
+      return SPM_ERR_CUDA;                                                                      \
+    }                                                                                           \
+  } while (0)
+
+template <typename T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t cap = 0;  // elements
+  cudaError_t ensure(size_t n, bool keep = false) {
+    if (n <= cap) return cudaSuccess;
+    size_t want = std::max(n, cap + cap / 2);
+    T *np = nullptr;
+    cudaError_t e = cudaMalloc(&np, want * sizeof(T) + 256);
+    if (e != cudaSuccess) return e;
+    if (keep && p && cap) cudaMemcpy(np, p, cap * sizeof(T), cudaMemcpyDeviceToDevice);
+    if (p) cudaFree(p);
+    p = np;
+    cap = want;
+    return cudaSuccess;
+  }
+  cudaError_t upload(const std::vector<T> &v) {
+    cudaError_t e = ensure(v.size() ? v.size() : 1);
+    if (e != cudaSuccess) return e;
+    if (!v.empty()) e = cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+template <typename T>
+struct PinBuf {
+  T *p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    size_t want = std::max(n, cap + cap / 2);
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMallocHost(&p, want * sizeof(T) + 64);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+bool valid_utf8(const char *s, size_t n) {
+  size_t i = 0;
+  const unsigned char *b = reinterpret_cast<const unsigned char *>(s);
+  while (i < n) {
+    const unsigned c = b[i];
+    size_t l = c < 0x80 ? 1 : (c & 0xE0) == 0xC0 ? 2 : (c & 0xF0) == 0xE0 ? 3 : (c & 0xF8) == 0xF0 ? 4 : 0;
+    if (!l || i + l > n) return false;
+    uint32_t cp = l == 1 ? c : l == 2 ? c & 0x1F : l == 3 ? c & 0x0F : c & 0x07;
+    for (size_t k = 1; k < l; ++k) {
+      if ((b[i + k] & 0xC0) != 0x80) return false;
+      cp = (cp << 6) | (b[i + k] & 0x3F);
+    }
+    if ((l == 2 && cp < 0x80) || (l == 3 && cp < 0x800) || (l == 4 && cp < 0x10000) || cp > 0x10FFFF ||
+        (cp >= 0xD800 && cp < 0xE000))
+      return false;
+    i += l;
+  }
+  return true;
+}
+
+}  // namespace
+
+struct spm_engine {
+  int device = 0;
+  int sm_count = 0;
+  size_t smem_optin = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  std::mutex mu;
+  mutable std::string err;
+
+  ModelData model;
+  DeviceTrie trie, user_trie;
+  float min_score = 0.f, max_score = 0.f;
+  int32_t unk_id = -1;
+  uint32_t max_expand_num = 3, max_expand_den = 1;  // worst-case normalized bytes per input byte
+  uint32_t charsmap_units = 0;
+  bool bpe_word_split = false;
+
+  // device tables
+  DevBuf<uint32_t> d_link, d_val, d_user_link, d_cm_units, d_cm_lead, d_cm_pair;
+  DevBuf<int32_t> d_id, d_cm_solo, d_byte_to_id;
+  DevBuf<uint8_t> d_cm_targets, d_types;
+  DevBuf<float> d_scores;
+  KModel km{};
+
+  // tuning
+  int G = 8;
+  int threads = 256;
+  uint32_t ncap = 256;
+  int ctas_per_sm = 1;
+
+  // per-call buffers (grow only)
+  DevBuf<uint8_t> d_bytes, d_tmp_norm, d_norm, d_long_scratch;
+  DevBuf<uint64_t> d_offsets;
+  DevBuf<int32_t> d_tmp_ids, d_ids;
+  DevBuf<uint32_t> d_tmp_tok_end, d_tok_end, d_tmp_n2o, d_n2o, d_sent_count, d_norm_len, d_deferred, d_long_list, d_ctrl32;
+  DevBuf<unsigned long long> d_sent_start, d_norm_start, d_id_offsets, d_norm_offsets, d_n2o_offsets, d_block_sums,
+      d_ctrl64, d_long_off;
+  PinBuf<int32_t> h_ids;
+  PinBuf<uint32_t> h_tok_end, h_n2o, h_ctrl32, h_deferred;
+  PinBuf<uint64_t> h_id_offsets, h_norm_offsets;
+  PinBuf<unsigned long long> h_ctrl64;
+  PinBuf<uint8_t> h_norm;
+
+  // stats of the last call
+  uint64_t last_launches = 0, last_h2d = 0, last_d2h = 0, last_deferred = 0;
+  float last_ms = 0.f, last_main_ms = 0.f;
+
+  void set_error(const std::string &m) const { err = m; }
+  int build_tables();
+  int upload_types();
+  int configure_kernel_attrs();
+  int run_device(const uint8_t *d_bytes_base, const uint64_t *d_offs, size_t n, uint64_t total_bytes, bool spans,
+                 int32_t *user_ids, uint64_t user_ids_cap, unsigned long long *user_id_offsets, uint64_t *total_ids,
+                 uint64_t *total_norm, cudaStream_t st);
+};
+
+// ---------------------------------------------------------------- model ----
+
+namespace {
+
+// ModelInterface::PieceToId for byte pieces (model_interface.cc:51-61,210-212)
+int32_t piece_to_id(const std::unordered_map<std::string, int32_t> &reserved,
+                    const std::unordered_map<std::string, int32_t> &pieces, int32_t unk, const std::string &p) {
+  auto it = reserved.find(p);
+  if (it != reserved.end()) return it->second;
+  auto it2 = pieces.find(p);
+  if (it2 != pieces.end()) return it2->second;
+  return unk;
+}
+
+}  // namespace
+
+int spm_engine::build_tables() {
+  ModelData &m = model;
+  if (m.model_type != SPM_UNIGRAM && m.model_type != SPM_BPE) {
+    set_error("only UNIGRAM and BPE models are on the accelerated path (model_factory.cc:25-48)");
+    return SPM_ERR_UNSUPPORTED;
+  }
+  const int V = m.vocab_size();
+  // ---- InitializePieces (model_interface.cc:63-151) ----
+  std::unordered_map<std::string, int32_t> pieces, reserved;
+  std::vector<bool> byte_found(256, false);
+  unk_id = -1;
+  for (int i = 0; i < V; ++i) {
+    const std::string p(m.piece(i), m.piece_len(i));
+    if (p.empty()) { set_error("piece must not be empty."); return SPM_ERR_MODEL; }
+    const uint8_t t = m.types[i];
+    const bool normal = t == SPM_NORMAL || t == SPM_USER_DEFINED || t == SPM_UNUSED;
+    if (!(normal ? pieces : reserved).emplace(p, i).second) { set_error(p + " is already defined."); return SPM_ERR_MODEL; }
+    if (t == SPM_UNKNOWN) {
+      if (unk_id >= 0) { set_error("unk is already defined."); return SPM_ERR_MODEL; }
+      unk_id = i;
+    }
+    if (t == SPM_BYTE) {
+      if (!m.byte_fallback) { set_error("byte piece " + p + " is found although `byte_fallback` is false."); return SPM_ERR_MODEL; }
+      int b = -1;
+      if (p.size() == 6) {
+        char canon[8];
+        for (int v = 0; v < 256 && b < 0; ++v) {
+          snprintf(canon, sizeof canon, "<0x%02X>", v);
+          if (p == canon) b = v;
+        }
+      }
+      if (b < 0) { set_error("byte piece " + p + " is invalid."); return SPM_ERR_MODEL; }
+      byte_found[b] = true;
+    }
+  }
+  if (unk_id < 0) { set_error("unk is not defined."); return SPM_ERR_MODEL; }
+  if (m.byte_fallback && std::find(byte_found.begin(), byte_found.end(), false) != byte_found.end()) {
+    set_error("there are not 256 byte pieces although `byte_fallback` is true.");
+    return SPM_ERR_MODEL;
+  }
+  // ---- unigram::Model ctor (unigram_model.cc:657-664): max starts at FLT_MIN (quirk Q3) ----
+  min_score = FLT_MAX;
+  max_score = FLT_MIN;
+  for (int i = 0; i < V; ++i)
+    if (m.types[i] == SPM_NORMAL) {
+      min_score = std::min(min_score, m.scores[i]);
+      max_score = std::max(max_score, m.scores[i]);
+    }
+  // ---- piece trie over pieces_ (unigram_model.cc:608-650 / bpe pieces_.find) ----
+  std::vector<TrieKey> keys, user_keys;
+  bool ws_only_at_front = true;
+  for (int i = 0; i < V; ++i) {
+    const uint8_t t = m.types[i];
+    if (!(t == SPM_NORMAL || t == SPM_USER_DEFINED || t == SPM_UNUSED)) continue;
+    const float s = m.scores[i];
+    const float w = m.model_type == SPM_UNIGRAM ? std::exp(s) : 1.0f / (1.0f + std::fabs(s));
+    const uint32_t kind = t == SPM_NORMAL ? kKindNormal : (t == SPM_USER_DEFINED ? kKindUserDefined : kKindUnused);
+    keys.push_back({m.piece(i), static_cast<uint32_t>(m.piece_len(i)), i, s, w, kind});
+    if (t == SPM_USER_DEFINED) user_keys.push_back({m.piece(i), static_cast<uint32_t>(m.piece_len(i)), i, 0.f, 1.f, kKindNormal});
+    if (!valid_utf8(m.piece(i), m.piece_len(i))) {
+      set_error("pieces that are not valid UTF-8 are not supported by the device path");
+      return SPM_ERR_UNSUPPORTED;
+    }
+    // U+2581 anywhere but at byte 0 defeats the per-word BPE decomposition
+    const std::string p(m.piece(i), m.piece_len(i));
+    if (p.find("\xE2\x96\x81", 1) != std::string::npos) ws_only_at_front = false;
+  }
+  bpe_word_split = ws_only_at_front;
+  std::string e;
+  if (!BuildDeviceTrie(keys, V, &trie, &e)) { set_error(e); return SPM_ERR_MODEL; }
+  if (trie.max_key_len > 255) { set_error("pieces longer than 255 bytes are not supported by the device path"); return SPM_ERR_UNSUPPORTED; }
+  if (!user_keys.empty() && !BuildDeviceTrie(user_keys, V, &user_trie, &e)) { set_error(e); return SPM_ERR_MODEL; }
+
+  // ---- byte fallback ids (sentencepiece_processor.cc:587-588) ----
+  std::vector<int32_t> byte_to_id(256, unk_id);
+  for (int b = 0; b < 256; ++b) {
+    char bp[8];
+    snprintf(bp, sizeof bp, "<0x%02X>", b);
+    byte_to_id[b] = piece_to_id(reserved, pieces, unk_id, bp);
+  }
+
+  // ---- precompiled charsmap (normalizer.cc:274-309) + fast-path tables ----
+  std::vector<uint32_t> cm_units, cm_lead(8, 0), cm_pair(128 * 256 / 32, 0);
+  std::vector<int32_t> cm_solo(128, -1);
+  std::vector<uint8_t> cm_targets(1, 0);
+  max_expand_num = m.escape_whitespaces ? 3 : 1;
+  max_expand_den = 1;
+  if (!m.charsmap.empty()) {
+    const std::string &blob = m.charsmap;
+    uint32_t trie_bytes = 0;
+    if (blob.size() <= 4) { set_error("Blob for normalization rule is broken."); return SPM_ERR_MODEL; }
+    memcpy(&trie_bytes, blob.data(), 4);
+    if (trie_bytes >= blob.size() - 4 + 4 || trie_bytes + 4 > blob.size()) { set_error("Trie data size exceeds the input blob size."); return SPM_ERR_MODEL; }
+    cm_units.resize(trie_bytes / 4);
+    memcpy(cm_units.data(), blob.data() + 4, cm_units.size() * 4);
+    cm_targets.assign(blob.begin() + 4 + trie_bytes, blob.end());
+    cm_targets.push_back(0);  // the blob's last target is NUL-terminated already; be safe
+    const size_t NU = cm_units.size();
+    auto off = [](uint32_t u) { return (u >> 10) << ((u & (1u << 9)) >> 6); };
+    auto label = [](uint32_t u) { return u & ((1u << 31) | 0xFFu); };
+    if (NU == 0) { set_error("Blob for normalization rule is broken."); return SPM_ERR_MODEL; }
+    // enumerate all keys by DFS over the double array: (node after the step, depth)
+    struct Fr { uint32_t node; uint32_t depth; uint32_t first; };
+    std::vector<Fr> stack;
+    const uint32_t root_next = 0 ^ off(cm_units[0]);
+    stack.push_back({root_next, 0, 256});
+    while (!stack.empty()) {
+      const Fr f = stack.back();
+      stack.pop_back();
+      for (uint32_t c = 0; c < 256; ++c) {
+        const uint32_t node = f.node ^ c;
+        if (node >= NU) continue;
+        const uint32_t unit = cm_units[node];
+        if (label(unit) != c) continue;
+        const uint32_t first = f.depth == 0 ? c : f.first;
+        if (f.depth == 0) cm_lead[c >> 5] |= 1u << (c & 31);
+        if (f.depth == 1 && f.first < 128) cm_pair[(f.first * 256 + c) >> 5] |= 1u << (c & 31);
+        const uint32_t nxt = node ^ off(unit);
+        if ((unit >> 8) & 1u) {
+          if (nxt >= NU) { set_error("charsmap trie is malformed"); return SPM_ERR_MODEL; }
+          const uint32_t value = cm_units[nxt] & 0x7FFFFFFFu;
+          if (value >= cm_targets.size()) { set_error("charsmap target offset out of range"); return SPM_ERR_MODEL; }
+          const size_t tl = strlen(reinterpret_cast<const char *>(cm_targets.data()) + value);
+          if (!valid_utf8(reinterpret_cast<const char *>(cm_targets.data()) + value, tl)) {
+            set_error("charsmap targets that are not valid UTF-8 are not supported by the device path");
+            return SPM_ERR_UNSUPPORTED;
+          }
+          if (f.depth == 0 && c < 128) cm_solo[c] = static_cast<int32_t>(value);
+          // expansion: every target byte may be a space that escapes to 3 bytes
+          size_t nsp = 0;
+          for (size_t k = 0; k < tl; ++k) nsp += cm_targets[value + k] == ' ';
+          const uint64_t out_bytes = tl + (m.escape_whitespaces ? 2 * nsp : 0);
+          const uint64_t klen = f.depth + 1;
+          if (out_bytes * max_expand_den > static_cast<uint64_t>(max_expand_num) * klen) {
+            max_expand_num = static_cast<uint32_t>(out_bytes);
+            max_expand_den = static_cast<uint32_t>(klen);
+          }
+        }
+        if (f.depth < 64) stack.push_back({nxt, f.depth + 1, first});
+      }
+    }
+  }
+  // malformed bytes expand 1 -> 3 (U+FFFD)
+  if (static_cast<uint64_t>(3) * max_expand_den > max_expand_num) { max_expand_num = 3; max_expand_den = 1; }
+  charsmap_units = static_cast<uint32_t>(cm_units.size());
+
+  // ---- upload ----
+  if (cudaSetDevice(device) != cudaSuccess) { set_error("cudaSetDevice failed"); return SPM_ERR_CUDA; }
+  CUDA_TRY(d_link.upload(trie.link));
+  CUDA_TRY(d_val.upload(trie.val));
+  CUDA_TRY(d_id.upload(trie.id));
+  if (!user_trie.link.empty()) CUDA_TRY(d_user_link.upload(user_trie.link));
+  if (cm_units.empty()) cm_units.push_back(0);
+  CUDA_TRY(d_cm_units.upload(cm_units));
+  CUDA_TRY(d_cm_targets.upload(cm_targets));
+  CUDA_TRY(d_cm_lead.upload(cm_lead));
+  CUDA_TRY(d_cm_pair.upload(cm_pair));
+  CUDA_TRY(d_cm_solo.upload(cm_solo));
+  CUDA_TRY(d_byte_to_id.upload(byte_to_id));
+  CUDA_TRY(d_scores.upload(m.scores));
+  CUDA_TRY(d_types.upload(m.types));
+
+  km.trie_link = d_link.p;
+  km.trie_val = d_val.p;
+  km.trie_id = d_id.p;
+  km.trie_units = static_cast<uint32_t>(trie.link.size());
+  km.match_slots = trie.max_matches_per_start + 1;
+  km.user_link = d_user_link.p;
+  km.cm_units = d_cm_units.p;
+  km.cm_nunits = charsmap_units;
+  km.cm_targets = d_cm_targets.p;
+  km.cm_lead = d_cm_lead.p;
+  km.cm_pair = d_cm_pair.p;
+  km.cm_solo = d_cm_solo.p;
+  km.byte_to_id = d_byte_to_id.p;
+  km.scores = d_scores.p;
+  km.types = d_types.p;
+  km.unk_id = unk_id;
+  km.unk_score = min_score - 10.0f;  // kUnkPenalty, unigram_model.cc:955
+  km.max_score = max_score;
+  km.model_type = m.model_type;
+  km.flags = (m.add_dummy_prefix ? kFlagAddDummyPrefix : 0) | (m.remove_extra_whitespaces ? kFlagRemoveExtraWs : 0) |
+             (m.escape_whitespaces ? kFlagEscapeWs : 0) | (m.treat_whitespace_as_suffix ? kFlagWsSuffix : 0) |
+             (m.byte_fallback ? kFlagByteFallback : 0) | (!user_trie.link.empty() ? kFlagHasUserSymbols : 0) |
+             (charsmap_units ? kFlagHasCharsmap : 0) | (bpe_word_split ? kFlagBpeWordSplit : 0);
+  return SPM_OK;
+}
+
+// Live piece types -> trie link words (kind bits) + types array.
+int spm_engine::upload_types() {
+  for (int i = 0; i < model.vocab_size(); ++i) {
+    const uint32_t u = trie.unit_of_id[i];
+    if (u == 0xFFFFFFFFu) continue;
+    const uint8_t t = model.types[i];
+    const uint32_t kind = t == SPM_NORMAL ? kKindNormal : (t == SPM_USER_DEFINED ? kKindUserDefined : kKindUnused);
+    trie.link[u] = (trie.link[u] & ~(3u << kLinkKindShift)) | (kind << kLinkKindShift);
+  }
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(d_link.upload(trie.link));
+  CUDA_TRY(d_types.upload(model.types));
+  return SPM_OK;
+}
+
+// -------------------------------------------------------------- launches ---
+
+namespace {
+
+struct LaunchGeom {
+  uint32_t hot_link, hot_val, tile_bytes, smem_bytes, tiles;
+};
+
+// Shared memory split: tiles first (threads/G of them), the rest goes to the hot
+// trie prefix (3:1 link:val, both multiples of 4 units for the 16-byte bulk copy).
+LaunchGeom plan_geometry(const spm_engine &e, bool spans, int G, int threads, uint32_t ncap, uint32_t K) {
+  LaunchGeom g{};
+  g.tiles = static_cast<uint32_t>(threads / G);
+  g.tile_bytes = tile_bytes_for(ncap, G, K, spans);
+  const size_t budget = e.smem_optin / std::max(1, e.ctas_per_sm) - (e.ctas_per_sm > 1 ? 1024 : 0);
+  const size_t fixed = 16 + static_cast<size_t>(g.tiles) * g.tile_bytes + 128;
+  size_t hot = budget > fixed ? budget - fixed : 0;
+  const uint32_t units = e.km.trie_units;
+  uint32_t hl = static_cast<uint32_t>(std::min<size_t>(units, (hot * 3 / 4) / 4)) & ~3u;
+  uint32_t hv = static_cast<uint32_t>(std::min<size_t>(units, (hot - static_cast<size_t>(hl) * 4) / 4)) & ~3u;
+  // if the whole link array fits, give the remainder to val
+  g.hot_link = hl;
+  g.hot_val = hv;
+  g.smem_bytes = static_cast<uint32_t>(16 + static_cast<size_t>(hl + hv) * 4 + static_cast<size_t>(g.tiles) * g.tile_bytes);
+  return g;
+}
+
+template <typename KernelT>
+cudaError_t set_smem(KernelT k, size_t bytes) {
+  return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+}
+
+}  // namespace
+
+int spm_engine::configure_kernel_attrs() {
+  const size_t mx = smem_optin;
+  CUDA_TRY(set_smem(encode_unigram_kernel<4, false>, mx));
+  CUDA_TRY(set_smem(encode_unigram_kernel<8, false>, mx));
+  CUDA_TRY(set_smem(encode_unigram_kernel<16, false>, mx));
+  CUDA_TRY(set_smem(encode_unigram_kernel<32, false>, mx));
+  CUDA_TRY(set_smem(encode_unigram_kernel<8, true>, mx));
+  CUDA_TRY(set_smem(encode_unigram_kernel<32, true>, mx));
+  CUDA_TRY(set_smem(encode_unigram_long_kernel<false>, mx));
+  CUDA_TRY(set_smem(encode_unigram_long_kernel<true>, mx));
+  CUDA_TRY(set_smem(encode_bpe_kernel<false>, mx));
+  CUDA_TRY(set_smem(encode_bpe_kernel<true>, mx));
+  return SPM_OK;
+}
+
+// Encodes a device-resident batch.  Outputs: ids (+offsets) either into the
+// engine's buffers (user_ids == nullptr) or the caller's.
+int spm_engine::run_device(const uint8_t *d_bytes_base, const uint64_t *d_offs, size_t n, uint64_t total_bytes,
+                           bool spans, int32_t *user_ids, uint64_t user_ids_cap, unsigned long long *user_id_offsets,
+                           uint64_t *total_ids, uint64_t *total_norm, cudaStream_t st) {
+  last_launches = 0;
+  last_deferred = 0;
+  const uint32_t n32 = static_cast<uint32_t>(n);
+  const bool bpe = model.model_type == SPM_BPE;
+  const int useG = bpe ? 32 : ((spans && G != 32) ? 8 : G);
+  const uint32_t K = km.match_slots;
+  LaunchGeom geom = plan_geometry(*this, spans, useG, threads, ncap, K);
+  if (bpe) {
+    // the BPE kernel owns a warp per sentence and its own scratch layout
+    geom.tiles = threads / 32;
+    geom.tile_bytes = bpe_tile_bytes(ncap, spans);
+    const size_t fixed = 16 + static_cast<size_t>(geom.tiles) * geom.tile_bytes + 128;
+    const size_t hot = smem_optin > fixed ? smem_optin - fixed : 0;
+    geom.hot_link = static_cast<uint32_t>(std::min<size_t>(km.trie_units, (hot * 3 / 4) / 4)) & ~3u;
+    geom.hot_val = static_cast<uint32_t>(std::min<size_t>(km.trie_units, (hot - static_cast<size_t>(geom.hot_link) * 4) / 4)) & ~3u;
+    geom.smem_bytes = static_cast<uint32_t>(16 + static_cast<size_t>(geom.hot_link + geom.hot_val) * 4 +
+                                            static_cast<size_t>(geom.tiles) * geom.tile_bytes);
+  }
+  if (geom.smem_bytes > smem_optin) { set_error("shared-memory geometry does not fit; lower smem_norm_cap"); return SPM_ERR_ARG; }
+  KModel M = km;
+  M.hot_link = geom.hot_link;
+  M.hot_val = geom.hot_val;
+
+  // capacities: ids <= normalized bytes; start with one id per input byte (+slack) and
+  // retry with the exact requirement when a pathological batch overflows.
+  unsigned long long tmp_cap = total_bytes + 4ull * n + 1024;
+  unsigned long long norm_cap = spans ? (total_bytes * 2 + 8ull * n + 1024) : 0;
+  CUDA_TRY(d_sent_start.ensure(n));
+  CUDA_TRY(d_sent_count.ensure(n));
+  CUDA_TRY(d_deferred.ensure(2 * n + 2));
+  CUDA_TRY(d_ctrl32.ensure(8));
+  CUDA_TRY(d_ctrl64.ensure(4));
+  CUDA_TRY(h_ctrl32.ensure(8));
+  CUDA_TRY(h_ctrl64.ensure(4));
+  if (spans) {
+    CUDA_TRY(d_norm_start.ensure(n));
+    CUDA_TRY(d_norm_len.ensure(n));
+  }
+
+  const int grid = sm_count * ctas_per_sm;
+  for (int attempt = 0; attempt < 3; ++attempt) {
+    CUDA_TRY(d_tmp_ids.ensure(tmp_cap));
+    if (spans) {
+      CUDA_TRY(d_tmp_tok_end.ensure(tmp_cap));
+      CUDA_TRY(d_tmp_norm.ensure(norm_cap));
+      CUDA_TRY(d_tmp_n2o.ensure(norm_cap));
+    }
+    CUDA_TRY(cudaMemsetAsync(d_ctrl32.p, 0, 8 * sizeof(uint32_t), st));
+    CUDA_TRY(cudaMemsetAsync(d_ctrl64.p, 0, 4 * sizeof(unsigned long long), st));
+    KBatch B{};
+    B.bytes = d_bytes_base;
+    B.offsets = d_offs;
+    B.n = n32;
+    B.tmp_ids = d_tmp_ids.p;
+    B.tmp_tok_end = d_tmp_tok_end.p;
+    B.tmp_cap = tmp_cap;
+    B.cursor = d_ctrl64.p;
+    B.sent_start = d_sent_start.p;
+    B.sent_count = d_sent_count.p;
+    B.tmp_norm = d_tmp_norm.p;
+    B.tmp_n2o = d_tmp_n2o.p;
+    B.tmp_norm_cap = norm_cap;
+    B.norm_start = d_norm_start.p;
+    B.norm_len = d_norm_len.p;
+    B.work_counter = d_ctrl32.p + 4;
+    B.deferred = d_deferred.p;
+    B.status = d_ctrl32.p;
+    B.ncap = ncap;
+    B.tile_bytes = geom.tile_bytes;
+
+    CUDA_TRY(cudaEventRecord(ev[0], st));
+    if (bpe) {
+      if (spans) encode_bpe_kernel<true><<<grid, threads, geom.smem_bytes, st>>>(M, B);
+      else encode_bpe_kernel<false><<<grid, threads, geom.smem_bytes, st>>>(M, B);
+    } else if (spans) {
+      if (useG == 32) encode_unigram_kernel<32, true><<<grid, threads, geom.smem_bytes, st>>>(M, B);
+      else encode_unigram_kernel<8, true><<<grid, threads, geom.smem_bytes, st>>>(M, B);
+    } else {
+      switch (useG) {
+        case 4: encode_unigram_kernel<4, false><<<grid, threads, geom.smem_bytes, st>>>(M, B); break;
+        case 8: encode_unigram_kernel<8, false><<<grid, threads, geom.smem_bytes, st>>>(M, B); break;
+        case 16: encode_unigram_kernel<16, false><<<grid, threads, geom.smem_bytes, st>>>(M, B); break;
+        default: encode_unigram_kernel<32, false><<<grid, threads, geom.smem_bytes, st>>>(M, B); break;
+      }
+    }
+    CUDA_TRY(cudaGetLastError());
+    ++last_launches;
+    CUDA_TRY(cudaEventRecord(ev[1], st));
+    CUDA_TRY(cudaMemcpyAsync(h_ctrl32.p, d_ctrl32.p, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(h_ctrl64.p, d_ctrl64.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    uint32_t n_def = h_ctrl32.p[0];
+    if (n_def) {
+      // ---- long sentences: warp per sentence, scratch slab in HBM ----
+      last_deferred = n_def;
+      CUDA_TRY(h_deferred.ensure(2 * static_cast<size_t>(n_def)));
+      CUDA_TRY(cudaMemcpyAsync(h_deferred.p, d_deferred.p, 2ull * n_def * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+      // lengths of the deferred sentences whose normalized size is unknown
+      std::vector<uint64_t> two(2);
+      std::vector<unsigned long long> offs(n_def + 1, 0);
+      CUDA_TRY(cudaStreamSynchronize(st));
+      for (uint32_t k = 0; k < n_def; ++k) {
+        uint32_t need = h_deferred.p[2 * k + 1];
+        if (need == 0) {
+          const uint32_t s = h_deferred.p[2 * k];
+          CUDA_TRY(cudaMemcpy(two.data(), d_offs + s, 16, cudaMemcpyDeviceToHost));
+          const uint64_t len = two[1] - two[0];
+          const uint64_t bound = (len * max_expand_num + max_expand_den - 1) / max_expand_den + 8;
+          if (bound > 0x7FFFFF00ull) { set_error("sentence too long for the device path"); return SPM_ERR_UNSUPPORTED; }
+          need = static_cast<uint32_t>(bound);
+        }
+        need += 8;
+        h_deferred.p[2 * k + 1] = need;
+        const uint32_t lk = bpe ? 1 : K;
+        const unsigned long long bytes = bpe ? bpe_tile_bytes(need, spans) : tile_bytes_for(need, 32, lk, spans);
+        offs[k + 1] = offs[k] + ((bytes + 255ull) & ~255ull);
+      }
+      CUDA_TRY(d_long_scratch.ensure(offs[n_def] + 256));
+      CUDA_TRY(d_long_list.ensure(2 * static_cast<size_t>(n_def)));
+      CUDA_TRY(d_long_off.ensure(n_def + 1));
+      CUDA_TRY(cudaMemcpyAsync(d_long_list.p, h_deferred.p, 2ull * n_def * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+      CUDA_TRY(cudaMemcpyAsync(d_long_off.p, offs.data(), (n_def + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+      B.long_list = d_long_list.p;
+      B.long_n = n_def;
+      B.long_scratch = d_long_scratch.p;
+      B.long_scratch_off = d_long_off.p;
+      const int lgrid = static_cast<int>(std::min<uint32_t>((n_def + 7) / 8, static_cast<uint32_t>(sm_count) * 4));
+      const uint32_t lsmem = 16 + (M.hot_link + M.hot_val) * 4;
+      if (bpe) {
+        if (spans) encode_bpe_long_kernel<true><<<lgrid, 256, lsmem, st>>>(M, B);
+        else encode_bpe_long_kernel<false><<<lgrid, 256, lsmem, st>>>(M, B);
+      } else {
+        if (spans) encode_unigram_long_kernel<true><<<lgrid, 256, lsmem, st>>>(M, B);
+        else encode_unigram_long_kernel<false><<<lgrid, 256, lsmem, st>>>(M, B);
+      }
+      CUDA_TRY(cudaGetLastError());
+      ++last_launches;
+      CUDA_TRY(cudaMemcpyAsync(h_ctrl32.p, d_ctrl32.p, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaMemcpyAsync(h_ctrl64.p, d_ctrl64.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    if (h_ctrl32.p[1]) {
+      set_error("encode failed: internal consistency check (status " + std::to_string(h_ctrl32.p[1]) + ")");
+      return SPM_ERR_ENCODE;
+    }
+    if (h_ctrl32.p[2]) {  // temporary buffers too small: cursors hold the exact requirement
+      tmp_cap = h_ctrl64.p[0] + 1024;
+      norm_cap = spans ? h_ctrl64.p[1] + 1024 : 0;
+      continue;
+    }
+    break;
+  }
+  if (h_ctrl32.p[2]) { set_error("temporary buffer overflow persisted"); return SPM_ERR_CAPACITY; }
+  const unsigned long long tot = h_ctrl64.p[0];
+  *total_ids = tot;
+  if (total_norm) *total_norm = spans ? h_ctrl64.p[1] : 0;
+
+  // ---- offsets (exclusive scan) + compaction into sentence order ----
+  const uint32_t nb = (n32 + kScanChunk - 1) / kScanChunk;
+  CUDA_TRY(d_block_sums.ensure(nb + 1));
+  int32_t *ids_out = user_ids;
+  unsigned long long *off_out = user_id_offsets;
+  if (!user_ids) {
+    CUDA_TRY(d_ids.ensure(tot + 1));
+    CUDA_TRY(d_id_offsets.ensure(n + 1));
+    ids_out = d_ids.p;
+    off_out = d_id_offsets.p;
+    user_ids_cap = d_ids.cap;
+    if (spans) CUDA_TRY(d_tok_end.ensure(tot + 1));
+  } else if (tot > user_ids_cap) {
+    set_error("ids_capacity too small: need " + std::to_string(tot));
+    return SPM_ERR_CAPACITY;
+  }
+  scan_block_sums_kernel<<<nb, 256, 0, st>>>(d_sent_count.p, n32, d_block_sums.p, 0);
+  scan_block_prefix_kernel<<<1, 1024, 0, st>>>(d_block_sums.p, nb, d_ctrl64.p + 2);
+  scan_write_gather_kernel<int32_t><<<nb, 256, 0, st>>>(d_sent_count.p, n32, d_block_sums.p, off_out, d_sent_start.p,
+                                                        d_tmp_ids.p, ids_out,
+                                                        spans ? d_tmp_tok_end.p : nullptr, spans ? d_tok_end.p : nullptr,
+                                                        user_ids_cap, 0);
+  last_launches += 3;
+  if (spans) {
+    const unsigned long long tn = h_ctrl64.p[1];  // sum(n_i + 1)
+    CUDA_TRY(d_norm.ensure(tn + 1));
+    CUDA_TRY(d_n2o.ensure(tn + 1));
+    CUDA_TRY(d_norm_offsets.ensure(n + 1));
+    CUDA_TRY(d_n2o_offsets.ensure(n + 1));
+    scan_block_sums_kernel<<<nb, 256, 0, st>>>(d_norm_len.p, n32, d_block_sums.p, 0);
+    scan_block_prefix_kernel<<<1, 1024, 0, st>>>(d_block_sums.p, nb, d_ctrl64.p + 3);
+    scan_write_gather_kernel<uint8_t><<<nb, 256, 0, st>>>(d_norm_len.p, n32, d_block_sums.p, d_norm_offsets.p,
+                                                          d_norm_start.p, d_tmp_norm.p, d_norm.p, nullptr, nullptr,
+                                                          d_norm.cap, 0);
+    // norm_to_orig has n_i + 1 entries per sentence: block sums of (len + 1)
+    scan_block_sums_kernel<<<nb, 256, 0, st>>>(d_norm_len.p, n32, d_block_sums.p, 1);
+    scan_block_prefix_kernel<<<1, 1024, 0, st>>>(d_block_sums.p, nb, d_ctrl64.p + 3);
+    scan_write_gather_kernel<uint32_t><<<nb, 256, 0, st>>>(d_norm_len.p, n32, d_block_sums.p, d_n2o_offsets.p,
+                                                           d_norm_start.p, d_tmp_n2o.p, d_n2o.p, nullptr, nullptr,
+                                                           d_n2o.cap, 1);
+    last_launches += 6;
+  }
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaEventRecord(ev[2], st));
+  return SPM_OK;
+}
+
+// ---------------------------------------------------------------- C ABI ----
+
+extern "C" {
+
+const char *spm_last_error(const spm_engine *e) {
+  if (e) return e->err.c_str();
+  return g_create_error.c_str();
+}
+
+static int create_common(spm_engine *e, int device, spm_engine **out) {
+  auto fail = [&](int code, const std::string &msg) {
+    std::lock_guard<std::mutex> lk(g_create_mu);
+    g_create_error = msg;
+    delete e;
+    return code;
+  };
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(SPM_ERR_CUDA, "no CUDA device available: this engine has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(SPM_ERR_ARG, "invalid device ordinal");
+  e->device = device;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(SPM_ERR_CUDA, "cudaGetDeviceProperties failed");
+  if (prop.major < 10) return fail(SPM_ERR_CUDA, "this build targets sm_100a (B200); found compute capability " +
+                                                      std::to_string(prop.major) + "." + std::to_string(prop.minor));
+  e->sm_count = prop.multiProcessorCount;
+  e->smem_optin = prop.sharedMemPerBlockOptin;
+  if (cudaSetDevice(device) != cudaSuccess) return fail(SPM_ERR_CUDA, "cudaSetDevice failed");
+  int rc = e->build_tables();
+  if (rc) return fail(rc, e->err);
+  if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(SPM_ERR_CUDA, "stream creation failed");
+  for (auto &ev : e->ev)
+    if (cudaEventCreate(&ev) != cudaSuccess) return fail(SPM_ERR_CUDA, "event creation failed");
+  rc = e->configure_kernel_attrs();
+  if (rc) return fail(rc, e->err);
+  *out = e;
+  return SPM_OK;
+}
+
+int spm_engine_create(const spm_model_desc *d, int device, spm_engine **out) {
+  if (!d || !out || d->vocab_size <= 0 || !d->piece_bytes || !d->piece_off || !d->scores || !d->types) {
+    std::lock_guard<std::mutex> lk(g_create_mu);
+    g_create_error = "spm_engine_create: null or empty model description";
+    return SPM_ERR_ARG;
+  }
+  spm_engine *e = new spm_engine();
+  ModelData &m = e->model;
+  m.model_type = d->model_type;
+  m.piece_off.assign(d->piece_off, d->piece_off + d->vocab_size + 1);
+  m.piece_bytes.assign(d->piece_bytes, d->piece_off[d->vocab_size]);
+  m.scores.assign(d->scores, d->scores + d->vocab_size);
+  m.types.assign(d->types, d->types + d->vocab_size);
+  m.byte_fallback = d->byte_fallback;
+  m.treat_whitespace_as_suffix = d->treat_whitespace_as_suffix;
+  m.add_dummy_prefix = d->add_dummy_prefix;
+  m.remove_extra_whitespaces = d->remove_extra_whitespaces;
+  m.escape_whitespaces = d->escape_whitespaces;
+  if (d->charsmap && d->charsmap_bytes) m.charsmap.assign(static_cast<const char *>(d->charsmap), d->charsmap_bytes);
+  return create_common(e, device, out);
+}
+
+int spm_engine_create_from_serialized(const void *model_proto, size_t len, int device, spm_engine **out) {
+  if (!model_proto || !len || !out) {
+    std::lock_guard<std::mutex> lk(g_create_mu);
+    g_create_error = "spm_engine_create_from_serialized: null argument";
+    return SPM_ERR_ARG;
+  }
+  spm_engine *e = new spm_engine();
+  std::string err;
+  if (!ParseModelProto(model_proto, len, &e->model, &err)) {
+    std::lock_guard<std::mutex> lk(g_create_mu);
+    g_create_error = err;
+    delete e;
+    return SPM_ERR_MODEL;
+  }
+  return create_common(e, device, out);
+}
+
+void spm_engine_destroy(spm_engine *e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  e->d_link.release(); e->d_val.release(); e->d_user_link.release(); e->d_cm_units.release(); e->d_cm_lead.release();
+  e->d_cm_pair.release(); e->d_id.release(); e->d_cm_solo.release(); e->d_byte_to_id.release(); e->d_cm_targets.release();
+  e->d_types.release(); e->d_scores.release(); e->d_bytes.release(); e->d_tmp_norm.release(); e->d_norm.release();
+  e->d_long_scratch.release(); e->d_offsets.release(); e->d_tmp_ids.release(); e->d_ids.release();
+  e->d_tmp_tok_end.release(); e->d_tok_end.release(); e->d_tmp_n2o.release(); e->d_n2o.release();
+  e->d_sent_count.release(); e->d_norm_len.release(); e->d_deferred.release(); e->d_long_list.release();
+  e->d_ctrl32.release(); e->d_sent_start.release(); e->d_norm_start.release(); e->d_id_offsets.release();
+  e->d_norm_offsets.release(); e->d_n2o_offsets.release(); e->d_block_sums.release(); e->d_ctrl64.release();
+  e->d_long_off.release();
+  e->h_ids.release(); e->h_tok_end.release(); e->h_n2o.release(); e->h_ctrl32.release(); e->h_deferred.release();
+  e->h_id_offsets.release(); e->h_norm_offsets.release(); e->h_ctrl64.release(); e->h_norm.release();
+  for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+int spm_engine_set_types(spm_engine *e, const uint8_t *types) {
+  if (!e || !types) return SPM_ERR_ARG;
+  std::lock_guard<std::mutex> lk(e->mu);
+  // the kinds CONTROL/UNKNOWN/BYTE never change (sentencepiece_processor.cc:311-316)
+  for (int i = 0; i < e->model.vocab_size(); ++i) {
+    const uint8_t o = e->model.types[i], t = types[i];
+    const bool on = o == SPM_NORMAL || o == SPM_USER_DEFINED || o == SPM_UNUSED;
+    const bool tn = t == SPM_NORMAL || t == SPM_USER_DEFINED || t == SPM_UNUSED;
+    if (on != tn || (!on && o != t)) { e->set_error("spm_engine_set_types: piece class changes are not allowed"); return SPM_ERR_ARG; }
+  }
+  e->model.types.assign(types, types + e->model.vocab_size());
+  return e->upload_types();
+}
+
+void *spm_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+  return p;
+}
+void spm_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+int spm_engine_get_info(const spm_engine *e, spm_engine_info *info) {
+  if (!e || !info) return SPM_ERR_ARG;
+  memset(info, 0, sizeof *info);
+  info->device = e->device;
+  info->sm_count = e->sm_count;
+  info->model_type = e->model.model_type;
+  info->vocab_size = e->model.vocab_size();
+  info->unk_id = e->unk_id;
+  info->min_score = e->min_score;
+  info->max_score = e->max_score;
+  info->trie_units = e->km.trie_units;
+  const LaunchGeom g = plan_geometry(*e, false, e->G, e->threads, e->ncap, e->km.match_slots);
+  info->trie_hot_units = g.hot_link;
+  info->charsmap_units = e->charsmap_units;
+  info->last_kernel_launches = e->last_launches;
+  info->last_kernel_ms = e->last_ms;
+  info->last_main_kernel_ms = e->last_main_ms;
+  info->last_h2d_bytes = e->last_h2d;
+  info->last_d2h_bytes = e->last_d2h;
+  info->last_deferred = e->last_deferred;
+  return SPM_OK;
+}
+
+int spm_engine_set_tuning(spm_engine *e, int lanes, int cap, int ctas) {
+  if (!e) return SPM_ERR_ARG;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (lanes) {
+    if (lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32) { e->set_error("lanes_per_sentence must be 4, 8, 16 or 32"); return SPM_ERR_ARG; }
+    e->G = lanes;
+  }
+  if (cap) {
+    if (cap < 64 || cap > 8192) { e->set_error("smem_norm_cap out of range"); return SPM_ERR_ARG; }
+    e->ncap = static_cast<uint32_t>(cap + 15) & ~15u;
+  }
+  if (ctas) {
+    // encoded as threads per CTA when >= 32
+    if (ctas >= 32) {
+      if (ctas % 32 || ctas > 512) { e->set_error("threads per CTA must be a multiple of 32, <= 512"); return SPM_ERR_ARG; }
+      e->threads = ctas;
+    } else {
+      e->ctas_per_sm = ctas;
+    }
+  }
+  return SPM_OK;
+}
+
+static void finish_timing(spm_engine *e) {
+  float a = 0.f, b = 0.f;
+  if (cudaEventElapsedTime(&a, e->ev[0], e->ev[1]) == cudaSuccess) e->last_main_ms = a;
+  if (cudaEventElapsedTime(&b, e->ev[0], e->ev[2]) == cudaSuccess) e->last_ms = b;
+}
+
+int spm_encode_ids_device(spm_engine *e, const char *d_bytes, const uint64_t *d_offsets, size_t n, uint64_t total_bytes,
+                          int32_t *d_ids, uint64_t ids_capacity, uint64_t *d_id_offsets, uint64_t *total_ids,
+                          void *stream) {
+  if (!e) return SPM_ERR_ARG;
+  std::lock_guard<std::mutex> lk(e->mu);
+  auto set_error = [&](const std::string &m) { e->set_error(m); };
+  if (!d_offsets || !d_id_offsets || !total_ids || (n && !d_bytes && total_bytes)) { e->set_error("null argument"); return SPM_ERR_ARG; }
+  if (n >= 0xFFFFFFF0ull) { e->set_error("too many sentences in one call"); return SPM_ERR_ARG; }
+  CUDA_TRY(cudaSetDevice(e->device));
+  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : e->stream;
+  *total_ids = 0;
+  if (n == 0) {
+    CUDA_TRY(cudaMemsetAsync(d_id_offsets, 0, sizeof(uint64_t), st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return SPM_OK;
+  }
+  e->last_h2d = e->last_d2h = 0;
+  const int rc = e->run_device(reinterpret_cast<const uint8_t *>(d_bytes), d_offsets, n, total_bytes, false, d_ids,
+                               ids_capacity, reinterpret_cast<unsigned long long *>(d_id_offsets), total_ids, nullptr, st);
+  if (rc) return rc;
+  CUDA_TRY(cudaStreamSynchronize(st));
+  finish_timing(e);
+  return SPM_OK;
+}
+
+static int encode_host(spm_engine *e, const char *bytes, const uint64_t *offsets, size_t n, bool spans,
+                       const int32_t **ids, const uint32_t **tok_end, const uint64_t **id_offsets,
+                       const char **normalized, const uint64_t **norm_offsets, const uint32_t **n2o) {
+  if (!e) return SPM_ERR_ARG;
+  std::lock_guard<std::mutex> lk(e->mu);
+  auto set_error = [&](const std::string &m) { e->set_error(m); };
+  if (!offsets || !ids || !id_offsets || (n && !bytes && offsets[n] != offsets[0])) { e->set_error("null argument"); return SPM_ERR_ARG; }
+  if (n >= 0xFFFFFFF0ull) { e->set_error("too many sentences in one call"); return SPM_ERR_ARG; }
+  CUDA_TRY(cudaSetDevice(e->device));
+  cudaStream_t st = e->stream;
+  CUDA_TRY(e->h_id_offsets.ensure(n + 1));
+  CUDA_TRY(e->h_ids.ensure(1));
+  if (n == 0) {
+    e->h_id_offsets.p[0] = 0;
+    *ids = e->h_ids.p;
+    *id_offsets = e->h_id_offsets.p;
+    if (spans) {
+      CUDA_TRY(e->h_norm_offsets.ensure(1)); CUDA_TRY(e->h_norm.ensure(1)); CUDA_TRY(e->h_tok_end.ensure(1)); CUDA_TRY(e->h_n2o.ensure(1));
+      e->h_norm_offsets.p[0] = 0;
+      *tok_end = e->h_tok_end.p; *normalized = reinterpret_cast<const char *>(e->h_norm.p);
+      *norm_offsets = e->h_norm_offsets.p; *n2o = e->h_n2o.p;
+    }
+    return SPM_OK;
+  }
+  for (size_t i = 0; i < n; ++i)
+    if (offsets[i + 1] < offsets[i]) { e->set_error("offsets must be non-decreasing"); return SPM_ERR_ARG; }
+  const uint64_t base = offsets[0];
+  const uint64_t total_bytes = offsets[n] - base;
+  CUDA_TRY(e->d_bytes.ensure(total_bytes + 64));
+  CUDA_TRY(e->d_offsets.ensure(n + 1));
+  if (total_bytes) CUDA_TRY(cudaMemcpyAsync(e->d_bytes.p, bytes + base, total_bytes, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(e->d_offsets.p, offsets, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+  e->last_h2d = total_bytes + (n + 1) * sizeof(uint64_t);
+  uint64_t tot = 0, totn = 0;
+  const int rc = e->run_device(e->d_bytes.p - base, e->d_offsets.p, n, total_bytes, spans, nullptr, 0, nullptr, &tot, &totn, st);
+  if (rc) return rc;
+  CUDA_TRY(e->h_ids.ensure(tot + 1));
+  if (tot) CUDA_TRY(cudaMemcpyAsync(e->h_ids.p, e->d_ids.p, tot * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(e->h_id_offsets.p, e->d_id_offsets.p, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+  e->last_d2h = tot * sizeof(int32_t) + (n + 1) * sizeof(uint64_t);
+  if (spans) {
+    CUDA_TRY(e->h_tok_end.ensure(tot + 1));
+    CUDA_TRY(e->h_norm.ensure(totn + 1));
+    CUDA_TRY(e->h_n2o.ensure(totn + 1));
+    CUDA_TRY(e->h_norm_offsets.ensure(n + 1));
+    if (tot) CUDA_TRY(cudaMemcpyAsync(e->h_tok_end.p, e->d_tok_end.p, tot * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(e->h_norm.p, e->d_norm.p, totn, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(e->h_n2o.p, e->d_n2o.p, totn * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(e->h_norm_offsets.p, e->d_norm_offsets.p, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    e->last_d2h += tot * 4 + totn * 5 + (n + 1) * 8;
+  }
+  CUDA_TRY(cudaStreamSynchronize(st));
+  finish_timing(e);
+  *ids = e->h_ids.p;
+  *id_offsets = e->h_id_offsets.p;
+  if (spans) {
+    *tok_end = e->h_tok_end.p;
+    *normalized = reinterpret_cast<const char *>(e->h_norm.p);
+    *norm_offsets = e->h_norm_offsets.p;
+    *n2o = e->h_n2o.p;
+  }
+  return SPM_OK;
+}
+
+int spm_encode_ids(spm_engine *e, const char *bytes, const uint64_t *offsets, size_t n, const int32_t **ids,
+                   const uint64_t **id_offsets) {
+  return encode_host(e, bytes, offsets, n, false, ids, nullptr, id_offsets, nullptr, nullptr, nullptr);
+}
+
+int spm_encode_spans(spm_engine *e, const char *bytes, const uint64_t *offsets, size_t n, const int32_t **ids,
+                     const uint32_t **tok_end, const uint64_t **id_offsets, const char **normalized,
+                     const uint64_t **norm_offsets, const uint32_t **n2o) {
+  if (!tok_end || !normalized || !norm_offsets || !n2o) return SPM_ERR_ARG;
+  return encode_host(e, bytes, offsets, n, true, ids, tok_end, id_offsets, normalized, norm_offsets, n2o);
+}
+
+}  // extern "C"

@@ -1,0 +1,148 @@
+"""Host-side mirror of the reference interface for the batched-encode path."""
+import ctypes
+
+import numpy as np
+
+from . import _capi
+
+
+def pack_sentences(sentences):
+    """list[bytes|str] -> (uint8[total], uint64[n+1])"""
+    bs = [s.encode("utf-8") if isinstance(s, str) else bytes(s) for s in sentences]
+    offs = np.zeros(len(bs) + 1, dtype=np.uint64)
+    if bs:
+        offs[1:] = np.cumsum([len(b) for b in bs], dtype=np.uint64)
+    buf = np.frombuffer(b"".join(bs), dtype=np.uint8) if bs else np.zeros(0, np.uint8)
+    return buf, offs
+
+
+class Engine:
+    """One engine = one model on one GPU (spm_engine in include/spm_b200.h)."""
+
+    def __init__(self, model_bytes, device=0):
+        self._lib = _capi.load()
+        h = ctypes.c_void_p()
+        rc = self._lib.spm_engine_create_from_serialized(model_bytes, len(model_bytes), device, ctypes.byref(h))
+        if rc:
+            raise RuntimeError(f"spm_engine_create failed ({rc}): {self._lib.spm_last_error(None).decode()}")
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.spm_engine_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc:
+            raise RuntimeError(f"spm_b200 error {rc}: {self._lib.spm_last_error(self._h).decode()}")
+
+    def info(self):
+        i = _capi.EngineInfo()
+        self._check(self._lib.spm_engine_get_info(self._h, ctypes.byref(i)))
+        return i
+
+    def set_tuning(self, lanes=0, cap=0, ctas=0):
+        self._check(self._lib.spm_engine_set_tuning(self._h, lanes, cap, ctas))
+
+    def set_types(self, types):
+        t = np.ascontiguousarray(types, dtype=np.uint8)
+        self._check(self._lib.spm_engine_set_types(self._h, t.ctypes.data))
+
+    def encode_packed(self, buf, offs, copy=True):
+        """Batch encode of a packed host buffer -> (ids int32[], id_offsets uint64[n+1])."""
+        n = len(offs) - 1
+        buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        offs = np.ascontiguousarray(offs, dtype=np.uint64)
+        ids = ctypes.c_void_p()
+        ido = ctypes.c_void_p()
+        self._check(self._lib.spm_encode_ids(self._h, buf.ctypes.data, offs.ctypes.data, n, ctypes.byref(ids),
+                                             ctypes.byref(ido)))
+        o = np.ctypeslib.as_array(ctypes.cast(ido, ctypes.POINTER(ctypes.c_uint64)), (n + 1,))
+        tot = int(o[n])
+        a = np.ctypeslib.as_array(ctypes.cast(ids, ctypes.POINTER(ctypes.c_int32)), (max(tot, 1),))[:tot]
+        return (a.copy(), o.copy()) if copy else (a, o)
+
+    def encode_packed_ptr(self, bytes_ptr, offs_ptr, n):
+        """Raw-pointer variant for benchmarks (pinned host memory): returns total ids."""
+        ids = ctypes.c_void_p()
+        ido = ctypes.c_void_p()
+        self._check(self._lib.spm_encode_ids(self._h, bytes_ptr, offs_ptr, n, ctypes.byref(ids), ctypes.byref(ido)))
+        o = np.ctypeslib.as_array(ctypes.cast(ido, ctypes.POINTER(ctypes.c_uint64)), (n + 1,))
+        return int(o[n]), ids.value, ido.value
+
+    def encode_spans(self, buf, offs):
+        """-> dict(ids, tok_end, id_offsets, normalized(bytes), norm_offsets, n2o)"""
+        n = len(offs) - 1
+        buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        offs = np.ascontiguousarray(offs, dtype=np.uint64)
+        p = [ctypes.c_void_p() for _ in range(6)]
+        self._check(self._lib.spm_encode_spans(self._h, buf.ctypes.data, offs.ctypes.data, n, *[ctypes.byref(x) for x in p]))
+        ido = np.ctypeslib.as_array(ctypes.cast(p[2], ctypes.POINTER(ctypes.c_uint64)), (n + 1,)).copy()
+        tot = int(ido[n])
+        no = np.ctypeslib.as_array(ctypes.cast(p[4], ctypes.POINTER(ctypes.c_uint64)), (n + 1,)).copy()
+        tn = int(no[n])
+        ids = np.ctypeslib.as_array(ctypes.cast(p[0], ctypes.POINTER(ctypes.c_int32)), (max(tot, 1),))[:tot].copy()
+        te = np.ctypeslib.as_array(ctypes.cast(p[1], ctypes.POINTER(ctypes.c_uint32)), (max(tot, 1),))[:tot].copy()
+        norm = ctypes.string_at(p[3], tn) if tn else b""
+        n2o = np.ctypeslib.as_array(ctypes.cast(p[5], ctypes.POINTER(ctypes.c_uint32)), (tn + n,)).copy()
+        return dict(ids=ids, tok_end=te, id_offsets=ido, normalized=norm, norm_offsets=no, n2o=n2o)
+
+    def encode_device(self, d_bytes_ptr, d_offs_ptr, n, total_bytes, d_ids_ptr, ids_cap, d_id_offs_ptr, stream=None):
+        """Device-resident batch (pointers are CUDA device pointers, e.g. torch data_ptr())."""
+        tot = ctypes.c_uint64()
+        self._check(self._lib.spm_encode_ids_device(self._h, d_bytes_ptr, d_offs_ptr, n, total_bytes, d_ids_ptr,
+                                                    ids_cap, d_id_offs_ptr, ctypes.byref(tot), stream))
+        return tot.value
+
+
+class SentencePieceProcessor:
+    """Mirror of the reference's encode API (same method names / argument meaning as
+    python/src/sentencepiece/__init__.py and src/sentencepiece_processor.h for this path)."""
+
+    def __init__(self, model_file=None, model_proto=None, device=0):
+        self._engine = None
+        if model_file is not None:
+            self.Load(model_file, device=device)
+        elif model_proto is not None:
+            self.LoadFromSerializedProto(model_proto, device=device)
+
+    # sentencepiece_processor.h:245
+    def Load(self, model_file, device=0):
+        with open(model_file, "rb") as f:
+            return self.LoadFromSerializedProto(f.read(), device=device)
+
+    # sentencepiece_processor.h:261
+    def LoadFromSerializedProto(self, serialized, device=0):
+        self._engine = Engine(bytes(serialized), device=device)
+        return True
+
+    def _require(self):
+        if self._engine is None:
+            raise RuntimeError("Model is not initialized.")  # sentencepiece_processor.cc:293-299
+
+    # sentencepiece_processor.h:458 + python batch entry sentencepiece.i:439-446
+    def EncodeAsIds(self, input):
+        self._require()
+        single = isinstance(input, (str, bytes))
+        buf, offs = pack_sentences([input] if single else input)
+        ids, ido = self._engine.encode_packed(buf, offs)
+        out = [ids[int(ido[i]):int(ido[i + 1])].tolist() for i in range(len(offs) - 1)]
+        return out[0] if single else out
+
+    def encode(self, input, out_type=int):
+        if out_type is not int:
+            raise NotImplementedError("use the C++ host layer for piece output")
+        return self.EncodeAsIds(input)
+
+    Encode = encode
+
+    @property
+    def engine(self):
+        self._require()
+        return self._engine
