@@ -1,0 +1,375 @@
+#!/usr/bin/env python3
+"""bench.py -- the driver's measurement contract for the batched subword-encode path.
+
+A "step" = one pass of the hot path (normalize -> unigram Viterbi / BPE merge -> ids)
+over one batch of synthetic sentences.  Default workload (N=1) is BASELINE.json
+configs[1]: 32k-vocab unigram model, 1,000,000 synthetic ~128-byte English sentences.
+
+  value : whole-job sentences/s with inputs already resident in HBM (device-pointer C ABI),
+          timed with CUDA events over exactly K steps, max over ranks.
+  e2e   : the same metric through the host-buffer C ABI (spm_encode_ids): pinned host input,
+          H2D + kernels + D2H of ids/offsets inside the timed region.
+  roofline : algorithmic bytes / encode-kernel time vs the measured HBM peak.
+  cpu_baseline : the reference's own Encode (oracle/_ref, all host threads) on a bounded sample.
+
+`--impl reference` times the unmodified reference on the host cores instead.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+WORKLOADS = {
+    # name: (model, corpus kind, description)
+    "unigram32k_en": ("uni32k", "en", "32k-vocab unigram Viterbi encode, synthetic ~128-byte English sentences"),
+    "bpe32k_en": ("bpe32k", "en", "32k-vocab BPE merge encode, synthetic ~128-byte English sentences"),
+    "bytefallback_mixed": ("mix_bf8k", "mixed", "byte-fallback unigram + NFKC on mixed CJK/emoji synthetic corpus"),
+}
+CORPUS_SEED = 20260922
+
+
+def model_bytes(name):
+    with open(os.path.join(ROOT, "tests", "golden", "models", name + ".model"), "rb") as f:
+        return f.read()
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def reference_rate(mb, buf, offs, threads, min_seconds=1.0):
+    """sentences/s of the unmodified reference (oracle/_ref) with `threads` host threads."""
+    from oracle import oracle_py
+    rm = oracle_py.RefModel(mb)
+    n = len(offs) - 1
+    rm.encode_count(buf, offs[: min(n, 2000) + 1], threads)  # warm caches / thread pool
+    best = None
+    t_all = time.perf_counter()
+    while True:
+        t0 = time.perf_counter()
+        rm.encode_count(buf, offs, threads)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+        if time.perf_counter() - t_all > min_seconds:
+            break
+    return n / best, best
+
+
+def run_reference_arm(args, rank, world):
+    """The reference's own CPU implementation on this box's host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    import corpus
+    from oracle import oracle_py
+    model, kind, desc = WORKLOADS[args.workload]
+    mb = model_bytes(model)
+    if not oracle_py.ref_available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref is not built on this box"}))
+        return
+    threads = host_threads()
+    # bounded sample of the same workload, sized so that K+W steps end within a few minutes
+    sample = min(args.sentences, max(20000, 12000 * threads))
+    g = corpus.CorpusGen()
+    buf, offs = g.fill(kind, CORPUS_SEED, sample)
+    rm = oracle_py.RefModel(mb)
+    for _ in range(args.warmup):
+        rm.encode_count(buf, offs, threads)
+    t0 = time.perf_counter()
+    ids = 0
+    for _ in range(args.steps):
+        ids = rm.encode_count(buf, offs, threads)
+    dt = time.perf_counter() - t0
+    rate = sample * args.steps / dt
+    in_bytes = int(offs[-1])
+    print(json.dumps({
+        "impl": "reference", "metric": "sentences_per_sec", "value": rate, "unit": "sentences/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64 scores / u8 text",
+        "data": "synthetic", "input_MBps": in_bytes * args.steps / dt / 1e6,
+        "config": {"workload": args.workload, "description": desc, "model": model + ".model",
+                   "sentences_per_step": sample, "mean_bytes_per_sentence": in_bytes / sample,
+                   "ids_per_sentence": ids / sample},
+        "cpu_baseline": {"value": rate, "unit": "sentences/s", "cores": threads, "kind": "reference",
+                         "sample": f"{sample} sentences of the workload per step, {threads} std::threads over "
+                                   "SentencePieceProcessor::Encode (oracle/_ref)"},
+        "e2e": {"value": rate, "unit": "sentences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="unigram32k_en", choices=sorted(WORKLOADS))
+    ap.add_argument("--sentences", type=int, default=1_000_000, help="sentences per GPU per step")
+    ap.add_argument("--lanes", type=int, default=0)
+    ap.add_argument("--cap", type=int, default=0)
+    ap.add_argument("--threads", type=int, default=0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-gather", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import corpus
+    from sentencepiece_b200 import Engine, _capi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback exists for the engine)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    model, kind, desc = WORKLOADS[args.workload]
+    mb = model_bytes(model)
+    eng = Engine(mb, device=local_rank)
+    if args.lanes or args.cap or args.threads:
+        eng.set_tuning(args.lanes, args.cap, args.threads)
+    lib = _capi.load()
+
+    # ---- this rank's shard, generated straight into pinned host memory ----
+    n = args.sentences
+    g = corpus.CorpusGen()
+    cap_bytes = (320 if kind == "en" else 512) * (n + 1)
+    pin_bytes = lib.spm_host_alloc(cap_bytes)
+    pin_offs = lib.spm_host_alloc(8 * (n + 1))
+    if not pin_bytes or not pin_offs:
+        raise SystemExit("pinned allocation failed")
+    hbuf = np.ctypeslib.as_array(ctypes.cast(pin_bytes, ctypes.POINTER(ctypes.c_uint8)), (cap_bytes,))
+    hoffs = np.ctypeslib.as_array(ctypes.cast(pin_offs, ctypes.POINTER(ctypes.c_uint64)), (n + 1,))
+    b, o = g.fill(kind, CORPUS_SEED, n, first=rank * n, out=hbuf)
+    hoffs[:] = o
+    total_bytes = int(o[-1])
+
+    # ---- device-resident copies (the "value" leg starts with inputs in HBM) ----
+    d_bytes = torch.empty(total_bytes + 64, dtype=torch.uint8, device=dev)
+    d_bytes[:total_bytes].copy_(torch.from_numpy(hbuf[:total_bytes]))
+    d_offs = torch.from_numpy(o.astype(np.int64)).to(dev)
+    ids_cap = total_bytes + 4 * n + 1024
+    d_ids = torch.empty(ids_cap, dtype=torch.int32, device=dev)
+    d_ido = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step_device():
+        return eng.encode_device(d_bytes.data_ptr(), d_offs.data_ptr(), n, total_bytes, d_ids.data_ptr(), ids_cap,
+                                 d_ido.data_ptr(), stream)
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    total_ids = 0
+    for _ in range(args.warmup):
+        total_ids = step_device()
+
+    # ---- timed: exactly K steps, CUDA events, barrier + synchronize on both sides ----
+    sampler = ClockSampler(local_rank)
+    sync_all()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    main_ms, all_ms, launches = [], [], 0
+    ev0.record()
+    for _ in range(args.steps):
+        total_ids = step_device()
+        info = eng.info()
+        main_ms.append(info.last_main_kernel_ms)
+        all_ms.append(info.last_kernel_ms)
+        launches += info.last_kernel_launches
+    ev1.record()
+    sync_all()
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * n * args.steps / (ms / 1e3)
+
+    # ---- e2e through the host-buffer C ABI (pinned host input; H2D and D2H inside) ----
+    e2e = None
+    if not args.no_e2e:
+        for _ in range(2):
+            eng.encode_packed_ptr(pin_bytes, pin_offs, n)
+        sync_all()
+        t0 = time.perf_counter()
+        h2d = d2h = 0
+        for _ in range(args.steps):
+            eng.encode_packed_ptr(pin_bytes, pin_offs, n)
+            info = eng.info()
+            h2d, d2h = info.last_h2d_bytes, info.last_d2h_bytes
+            launches_e2e = info.last_kernel_launches
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": world * n * args.steps / dt, "unit": "sentences/s", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": dt / args.steps * 1e3,
+               "api": "spm_encode_ids (host buffers, pinned input)", "timer": "host wall clock around synchronous calls"}
+
+    # ---- NCCL gather of the packed id buffers to rank 0 (the path's only exchange) ----
+    gather = None
+    if world > 1 and not args.no_gather:
+        cnt = torch.tensor([total_ids], dtype=torch.int64, device=dev)
+        cnts = [torch.zeros_like(cnt) for _ in range(world)]
+        dist.all_gather(cnts, cnt)
+        mx = int(max(int(c.item()) for c in cnts))
+        send = d_ids[:mx]
+        recv = [torch.empty(mx, dtype=torch.int32, device=dev) for _ in range(world)] if rank == 0 else None
+        for _ in range(2):
+            dist.gather(send, recv, dst=0)
+        sync_all()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(5):
+            dist.gather(send, recv, dst=0)
+        g1.record()
+        sync_all()
+        gms = g0.elapsed_time(g1) / 5
+        t = torch.tensor([gms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        gather = {"ms_per_step": float(t.item()), "bytes_to_rank0": mx * 4 * (world - 1),
+                  "how": "torch.distributed.gather (NCCL) of padded int32 id buffers over NVLink"}
+
+    if rank == 0:
+        # ---- roofline of the dominant kernel (the encode kernel) ----
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak = json.load(open(peaks_path))["hbm_gbs"]
+            peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        alg_bytes = total_bytes + 8 * n + 4 * total_ids  # input + 4 + 4*ids + 4 per sentence
+        kernel_ms = statistics.mean(main_ms)
+        achieved = alg_bytes / (kernel_ms / 1e3) / 1e9
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": None, "kernel": "encode_%s_kernel" % ("bpe" if "bpe" in model else "unigram"),
+                    "kernel_ms": kernel_ms, "all_kernels_ms": statistics.mean(all_ms),
+                    "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                    "note": "latency/L2-bound integer path: ~570 dependent trie lookups per sentence vs ~250 B of "
+                            "compulsory HBM traffic (SURVEY 8d 'honest expectation')"}
+        cpu = None
+        if not args.no_cpu:
+            from oracle import oracle_py
+            threads = host_threads()
+            sample = min(n, max(20000, 12000 * threads))
+            if oracle_py.ref_available():
+                rate, secs = reference_rate(mb, hbuf, o[: sample + 1], threads, min_seconds=3.0)
+                rate1, _ = reference_rate(mb, hbuf, o[: min(sample, 40000) + 1], 1, min_seconds=1.0)
+                cpu = {"value": rate, "unit": "sentences/s", "cores": threads, "kind": "reference",
+                       "single_thread_value": rate1,
+                       "sample": f"first {sample} sentences of the workload, best of repeats over ~3 s; unmodified "
+                                 "reference Encode via oracle/_ref with std::threads"}
+            else:
+                om = oracle_py.OracleModel(mb)
+                sample = min(n, 100000)
+                t0 = time.perf_counter()
+                om.encode_batch(hbuf, o[: sample + 1])
+                dt = time.perf_counter() - t0
+                cpu = {"value": sample / dt, "unit": "sentences/s", "cores": 1, "kind": "port",
+                       "sample": f"first {sample} sentences, scalar C oracle (oracle/_ref missing)"}
+        out = {
+            "metric": "sentences_per_sec", "value": value, "unit": "sentences/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8 text / int32 ids / f32+f64 scores",
+            "data": "synthetic", "input_MBps": world * total_bytes * args.steps / (ms / 1e3) / 1e6,
+            "config": {"workload": args.workload, "description": desc, "model": model + ".model",
+                       "sentences_per_gpu_per_step": n, "mean_bytes_per_sentence": total_bytes / n,
+                       "ids_per_sentence": total_ids / n, "parallelism": f"sentence-sharded x{world}",
+                       "l2": "inputs+outputs per step (%.0f MB) exceed the 126 MB L2" % ((total_bytes + 4 * total_ids) / 1e6),
+                       "tuning": {"lanes": args.lanes, "cap": args.cap, "threads": args.threads}},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+        }
+        if gather:
+            out["gather"] = gather
+        print(json.dumps(out))
+    lib.spm_host_free(pin_bytes)
+    lib.spm_host_free(pin_offs)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -14,6 +14,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -399,6 +400,7 @@ LaunchGeom plan_geometry(const spm_engine &e, bool spans, int G, int threads, ui
   const size_t budget = e.smem_optin / std::max(1, e.ctas_per_sm) - (e.ctas_per_sm > 1 ? 1024 : 0);
   const size_t fixed = 16 + static_cast<size_t>(g.tiles) * g.tile_bytes + 128;
   size_t hot = budget > fixed ? budget - fixed : 0;
+  if (const char *lim = getenv("SPM_B200_HOT_LIMIT")) hot = std::min<size_t>(hot, strtoull(lim, nullptr, 10));  // experiments
   const uint32_t units = e.km.trie_units;
   uint32_t hl = static_cast<uint32_t>(std::min<size_t>(units, (hot * 3 / 4) / 4)) & ~3u;
   uint32_t hv = static_cast<uint32_t>(std::min<size_t>(units, (hot - static_cast<size_t>(hl) * 4) / 4)) & ~3u;
