@@ -27,6 +27,7 @@
 #include "kernels.cuh"
 #include "model_reader.h"
 #include "trie_builder.h"
+#include "unigram_warp.cuh"
 
 using namespace spm_b200;
 
@@ -133,8 +134,8 @@ struct spm_engine {
   KModel km{};
 
   // tuning
-  int G = 8;
-  int threads = 256;
+  int G = 32;
+  int threads = 768;
   uint32_t ncap = 256;
   int ctas_per_sm = 1;
 
@@ -428,6 +429,8 @@ int spm_engine::configure_kernel_attrs() {
   CUDA_TRY(set_smem(encode_unigram_kernel<32, true>, mx));
   CUDA_TRY(set_smem(encode_unigram_long_kernel<false>, mx));
   CUDA_TRY(set_smem(encode_unigram_long_kernel<true>, mx));
+  CUDA_TRY(set_smem(encode_unigram_warp_kernel<512>, mx));
+  CUDA_TRY(set_smem(encode_unigram_warp_kernel<1024>, mx));
   CUDA_TRY(set_smem(encode_bpe_kernel<false>, mx));
   CUDA_TRY(set_smem(encode_bpe_kernel<true>, mx));
   return SPM_OK;
@@ -443,12 +446,16 @@ int spm_engine::run_device(const uint8_t *d_bytes_base, const uint64_t *d_offs, 
   const uint32_t n32 = static_cast<uint32_t>(n);
   const bool bpe = model.model_type == SPM_BPE;
   const int useG = bpe ? 32 : ((spans && G != 32) ? 8 : G);
+  const int tile_threads = std::min(threads, 512);
   const uint32_t K = km.match_slots;
-  LaunchGeom geom = plan_geometry(*this, spans, useG, threads, ncap, K);
-  if (bpe) {
-    // the BPE kernel owns a warp per sentence and its own scratch layout
-    geom.tiles = threads / 32;
-    geom.tile_bytes = bpe_tile_bytes(ncap, spans);
+  LaunchGeom geom = plan_geometry(*this, spans, useG, tile_threads, ncap, K);
+  // fast unigram path: warp per sentence, register-resident Viterbi window
+  const bool warp_path = !bpe && !spans && trie.max_key_len <= 32 && G == 32 && !getenv("SPM_B200_TILE_KERNEL");
+  const int launch_threads = warp_path ? threads : tile_threads;
+  if (bpe || warp_path) {
+    // these kernels own a warp per sentence and their own scratch layout
+    geom.tiles = launch_threads / 32;
+    geom.tile_bytes = bpe ? bpe_tile_bytes(ncap, spans) : warp_bytes_for(ncap, K);
     const size_t fixed = 16 + static_cast<size_t>(geom.tiles) * geom.tile_bytes + 128;
     const size_t hot = smem_optin > fixed ? smem_optin - fixed : 0;
     geom.hot_link = static_cast<uint32_t>(std::min<size_t>(km.trie_units, (hot * 3 / 4) / 4)) & ~3u;
@@ -510,17 +517,20 @@ int spm_engine::run_device(const uint8_t *d_bytes_base, const uint64_t *d_offs, 
 
     CUDA_TRY(cudaEventRecord(ev[0], st));
     if (bpe) {
-      if (spans) encode_bpe_kernel<true><<<grid, threads, geom.smem_bytes, st>>>(M, B);
-      else encode_bpe_kernel<false><<<grid, threads, geom.smem_bytes, st>>>(M, B);
+      if (spans) encode_bpe_kernel<true><<<grid, tile_threads, geom.smem_bytes, st>>>(M, B);
+      else encode_bpe_kernel<false><<<grid, tile_threads, geom.smem_bytes, st>>>(M, B);
+    } else if (warp_path) {
+      if (threads <= 512) encode_unigram_warp_kernel<512><<<grid, threads, geom.smem_bytes, st>>>(M, B);
+      else encode_unigram_warp_kernel<1024><<<grid, threads, geom.smem_bytes, st>>>(M, B);
     } else if (spans) {
-      if (useG == 32) encode_unigram_kernel<32, true><<<grid, threads, geom.smem_bytes, st>>>(M, B);
-      else encode_unigram_kernel<8, true><<<grid, threads, geom.smem_bytes, st>>>(M, B);
+      if (useG == 32) encode_unigram_kernel<32, true><<<grid, tile_threads, geom.smem_bytes, st>>>(M, B);
+      else encode_unigram_kernel<8, true><<<grid, tile_threads, geom.smem_bytes, st>>>(M, B);
     } else {
       switch (useG) {
-        case 4: encode_unigram_kernel<4, false><<<grid, threads, geom.smem_bytes, st>>>(M, B); break;
-        case 8: encode_unigram_kernel<8, false><<<grid, threads, geom.smem_bytes, st>>>(M, B); break;
-        case 16: encode_unigram_kernel<16, false><<<grid, threads, geom.smem_bytes, st>>>(M, B); break;
-        default: encode_unigram_kernel<32, false><<<grid, threads, geom.smem_bytes, st>>>(M, B); break;
+        case 4: encode_unigram_kernel<4, false><<<grid, tile_threads, geom.smem_bytes, st>>>(M, B); break;
+        case 8: encode_unigram_kernel<8, false><<<grid, tile_threads, geom.smem_bytes, st>>>(M, B); break;
+        case 16: encode_unigram_kernel<16, false><<<grid, tile_threads, geom.smem_bytes, st>>>(M, B); break;
+        default: encode_unigram_kernel<32, false><<<grid, tile_threads, geom.smem_bytes, st>>>(M, B); break;
       }
     }
     CUDA_TRY(cudaGetLastError());
@@ -591,13 +601,16 @@ int spm_engine::run_device(const uint8_t *d_bytes_base, const uint64_t *d_offs, 
     break;
   }
   if (h_ctrl32.p[2]) { set_error("temporary buffer overflow persisted"); return SPM_ERR_CAPACITY; }
-  const unsigned long long tot = h_ctrl64.p[0];
-  *total_ids = tot;
-  if (total_norm) *total_norm = spans ? h_ctrl64.p[1] : 0;
-
   // ---- offsets (exclusive scan) + compaction into sentence order ----
   const uint32_t nb = (n32 + kScanChunk - 1) / kScanChunk;
   CUDA_TRY(d_block_sums.ensure(nb + 1));
+  scan_block_sums_kernel<<<nb, 256, 0, st>>>(d_sent_count.p, n32, d_block_sums.p, 0);
+  scan_block_prefix_kernel<<<1, 1024, 0, st>>>(d_block_sums.p, nb, d_ctrl64.p + 2);
+  CUDA_TRY(cudaMemcpyAsync(h_ctrl64.p, d_ctrl64.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  const unsigned long long tot = h_ctrl64.p[2];  // the cursor over-counts (chunked claims); the scan is exact
+  *total_ids = tot;
+  if (total_norm) *total_norm = spans ? h_ctrl64.p[1] : 0;
   int32_t *ids_out = user_ids;
   unsigned long long *off_out = user_id_offsets;
   if (!user_ids) {
@@ -611,8 +624,6 @@ int spm_engine::run_device(const uint8_t *d_bytes_base, const uint64_t *d_offs, 
     set_error("ids_capacity too small: need " + std::to_string(tot));
     return SPM_ERR_CAPACITY;
   }
-  scan_block_sums_kernel<<<nb, 256, 0, st>>>(d_sent_count.p, n32, d_block_sums.p, 0);
-  scan_block_prefix_kernel<<<1, 1024, 0, st>>>(d_block_sums.p, nb, d_ctrl64.p + 2);
   scan_write_gather_kernel<int32_t><<<nb, 256, 0, st>>>(d_sent_count.p, n32, d_block_sums.p, off_out, d_sent_start.p,
                                                         d_tmp_ids.p, ids_out,
                                                         spans ? d_tmp_tok_end.p : nullptr, spans ? d_tok_end.p : nullptr,
@@ -798,7 +809,7 @@ int spm_engine_set_tuning(spm_engine *e, int lanes, int cap, int ctas) {
   if (ctas) {
     // encoded as threads per CTA when >= 32
     if (ctas >= 32) {
-      if (ctas % 32 || ctas > 512) { e->set_error("threads per CTA must be a multiple of 32, <= 512"); return SPM_ERR_ARG; }
+      if (ctas % 32 || ctas > 1024) { e->set_error("threads per CTA must be a multiple of 32, <= 1024"); return SPM_ERR_ARG; }
       e->threads = ctas;
     } else {
       e->ctas_per_sm = ctas;

@@ -30,7 +30,7 @@ d_ido = torch.empty(n + 1, dtype=torch.int64, device=dev)
 if configs:
     grid = [tuple(int(x) for x in c.split(",")) for c in configs]
 else:
-    grid = [(G, thr, capn) for G, thr, capn in itertools.product((4, 8, 16, 32), (256, 384, 512), (256,))]
+    grid = [(32, thr, capn) for thr, capn in itertools.product((512, 768, 1024), (224, 256))]
 ref = None
 for G, thr, capn in grid:
     try:
