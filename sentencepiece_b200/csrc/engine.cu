@@ -366,6 +366,8 @@ int spm_engine::build_tables() {
              (m.escape_whitespaces ? kFlagEscapeWs : 0) | (m.treat_whitespace_as_suffix ? kFlagWsSuffix : 0) |
              (m.byte_fallback ? kFlagByteFallback : 0) | (!user_trie.link.empty() ? kFlagHasUserSymbols : 0) |
              (charsmap_units ? kFlagHasCharsmap : 0) | (bpe_word_split ? kFlagBpeWordSplit : 0);
+  for (uint8_t t : m.types)
+    if (t == SPM_UNUSED) km.flags |= kFlagHasUnused;
   return SPM_OK;
 }
 
@@ -378,6 +380,9 @@ int spm_engine::upload_types() {
     const uint32_t kind = t == SPM_NORMAL ? kKindNormal : (t == SPM_USER_DEFINED ? kKindUserDefined : kKindUnused);
     trie.link[u] = (trie.link[u] & ~(3u << kLinkKindShift)) | (kind << kLinkKindShift);
   }
+  bool any_unused = false;
+  for (uint8_t t : model.types) any_unused |= t == SPM_UNUSED;
+  km.flags = (km.flags & ~kFlagHasUnused) | (any_unused ? kFlagHasUnused : 0u);
   CUDA_TRY(cudaSetDevice(device));
   CUDA_TRY(d_link.upload(trie.link));
   CUDA_TRY(d_types.upload(model.types));
@@ -433,6 +438,8 @@ int spm_engine::configure_kernel_attrs() {
   CUDA_TRY(set_smem(encode_unigram_warp_kernel<1024>, mx));
   CUDA_TRY(set_smem(encode_bpe_kernel<false>, mx));
   CUDA_TRY(set_smem(encode_bpe_kernel<true>, mx));
+  CUDA_TRY(set_smem(encode_bpe_long_kernel<false>, mx));
+  CUDA_TRY(set_smem(encode_bpe_long_kernel<true>, mx));
   return SPM_OK;
 }
 
