@@ -1,0 +1,259 @@
+// host/sentencepiece_processor.cc -- see the header.  All heavy lifting is behind the C ABI.
+#include "host/sentencepiece_processor.h"
+
+#include <algorithm>
+#include <cstring>
+#include <fstream>
+#include <set>
+#include <sstream>
+#include <unordered_map>
+
+#include "model_reader.h"
+#include "spm_b200.h"
+
+namespace sentencepiece {
+
+struct SentencePieceProcessor::Impl {
+  spm_b200::ModelData model;
+  std::vector<std::string> pieces;
+  std::unordered_map<std::string, int> piece_to_id;
+  std::vector<uint8_t> loaded_types;
+};
+
+namespace {
+util::Status Internal(const std::string &m) { return util::Status(util::StatusCode::kInternal, m); }
+util::Status FromEngine(const spm_engine *e, int rc) {
+  if (rc == 0) return util::OkStatus();
+  return Internal(std::string("spm_b200(") + std::to_string(rc) + "): " + spm_last_error(e));
+}
+}  // namespace
+
+SentencePieceProcessor::SentencePieceProcessor() : impl_(new Impl) {}
+SentencePieceProcessor::~SentencePieceProcessor() {
+  if (engine_) spm_engine_destroy(engine_);
+}
+
+util::Status SentencePieceProcessor::status() const {
+  if (!engine_) return Internal("Model is not initialized.");  // sentencepiece_processor.cc:293-299
+  return util::OkStatus();
+}
+
+util::Status SentencePieceProcessor::Load(std::string_view filename) {
+  std::ifstream f(std::string(filename), std::ios::binary);
+  if (!f) return util::Status(util::StatusCode::kNotFound, "\"" + std::string(filename) + "\": No such file or directory");
+  std::stringstream ss;
+  ss << f.rdbuf();
+  return LoadFromSerializedProto(ss.str());
+}
+
+util::Status SentencePieceProcessor::LoadFromSerializedProto(std::string_view serialized) {
+  std::string err;
+  if (!spm_b200::ParseModelProto(serialized.data(), serialized.size(), &impl_->model, &err)) return Internal(err);
+  if (engine_) { spm_engine_destroy(engine_); engine_ = nullptr; }
+  const int rc = spm_engine_create_from_serialized(serialized.data(), serialized.size(), device_, &engine_);
+  if (rc) { engine_ = nullptr; return FromEngine(nullptr, rc); }
+  const auto &m = impl_->model;
+  impl_->pieces.clear();
+  impl_->piece_to_id.clear();
+  unk_id_ = -1;
+  for (int i = 0; i < m.vocab_size(); ++i) {
+    impl_->pieces.emplace_back(m.piece(i), m.piece_len(i));
+    impl_->piece_to_id.emplace(impl_->pieces.back(), i);  // first definition wins, like InsertIfNotPresent
+    if (m.types[i] == SPM_UNKNOWN) unk_id_ = i;
+  }
+  impl_->loaded_types = m.types;
+  extra_.clear();
+  return util::OkStatus();
+}
+
+int SentencePieceProcessor::GetPieceSize() const { return static_cast<int>(impl_->pieces.size()); }
+int SentencePieceProcessor::PieceToId(std::string_view piece) const {
+  const auto it = impl_->piece_to_id.find(std::string(piece));
+  return it == impl_->piece_to_id.end() ? unk_id_ : it->second;  // model_interface.cc:51-61
+}
+const std::string &SentencePieceProcessor::IdToPiece(int id) const {
+  static const std::string kEmpty;
+  return id >= 0 && id < GetPieceSize() ? impl_->pieces[id] : kEmpty;
+}
+int SentencePieceProcessor::bos_id() const {
+  const int id = PieceToId(impl_->model.bos_piece);
+  return id == unk_id_ ? -1 : id;
+}
+int SentencePieceProcessor::eos_id() const {
+  const int id = PieceToId(impl_->model.eos_piece);
+  return id == unk_id_ ? -1 : id;
+}
+
+// ParseExtraOptions, sentencepiece_processor.cc:1067-1101
+util::Status SentencePieceProcessor::SetEncodeExtraOptions(std::string_view extra_option) {
+  extra_.clear();
+  if (extra_option.empty()) return util::OkStatus();
+  if (!engine_) return status();
+  size_t pos = 0;
+  while (pos <= extra_option.size()) {
+    size_t nxt = extra_option.find(':', pos);
+    if (nxt == std::string_view::npos) nxt = extra_option.size();
+    const std::string s(extra_option.substr(pos, nxt - pos));
+    if (s == "bos") {
+      if (IsUnknown(PieceToId(impl_->model.bos_piece))) return Internal("id for `" + impl_->model.bos_piece + "` is not defined.");
+      extra_.push_back(BOS);
+    } else if (s == "eos") {
+      if (IsUnknown(PieceToId(impl_->model.eos_piece))) return Internal("id for `" + impl_->model.eos_piece + "` is not defined.");
+      extra_.push_back(EOS);
+    } else if (s == "reverse") {
+      extra_.push_back(REVERSE);
+    } else if (s == "unk" || s == "unk_piece") {
+      extra_.push_back(UNK_PIECE);
+    } else {
+      extra_.clear();
+      return Internal("option \"" + s + "\" is not available.");
+    }
+    pos = nxt + 1;
+  }
+  return util::OkStatus();
+}
+
+// sentencepiece_processor.cc:301-330: pieces of one character are always kept
+util::Status SentencePieceProcessor::SetVocabulary(const std::vector<std::string_view> &valid_vocab) {
+  if (!engine_) return status();
+  auto &m = impl_->model;
+  const std::set<std::string_view> vocab(valid_vocab.begin(), valid_vocab.end());
+  static const unsigned char kLen[16] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 2, 2, 3, 4};
+  for (int i = 0; i < m.vocab_size(); ++i) {
+    uint8_t &t = m.types[i];
+    if (t == SPM_CONTROL || t == SPM_UNKNOWN || t == SPM_USER_DEFINED) continue;
+    const std::string &p = impl_->pieces[i];
+    const bool one_char = kLen[static_cast<unsigned char>(p[0]) >> 4] == p.size();
+    if (t == SPM_BYTE) continue;  // byte pieces never enter pieces_; their class is fixed
+    t = (vocab.count(p) || one_char) ? SPM_NORMAL : SPM_UNUSED;
+  }
+  return FromEngine(engine_, spm_engine_set_types(engine_, m.types.data()));
+}
+
+util::Status SentencePieceProcessor::ResetVocabulary() {
+  if (!engine_) return status();
+  for (auto &t : impl_->model.types)
+    if (t == SPM_UNUSED) t = SPM_NORMAL;
+  return FromEngine(engine_, spm_engine_set_types(engine_, impl_->model.types.data()));
+}
+
+util::Status SentencePieceProcessor::EncodePacked(const char *bytes, const uint64_t *offsets, size_t n,
+                                                  const int32_t **ids, const uint64_t **id_offsets) const {
+  if (!engine_) return status();
+  return FromEngine(engine_, spm_encode_ids(engine_, bytes, offsets, n, ids, id_offsets));
+}
+
+namespace {
+void Pack(const std::vector<std::string_view> &in, std::string *bytes, std::vector<uint64_t> *offs) {
+  size_t total = 0;
+  for (const auto &s : in) total += s.size();
+  bytes->clear();
+  bytes->reserve(total);
+  offs->assign(1, 0);
+  offs->reserve(in.size() + 1);
+  for (const auto &s : in) {
+    bytes->append(s.data(), s.size());
+    offs->push_back(bytes->size());
+  }
+}
+}  // namespace
+
+util::Status SentencePieceProcessor::Encode(const std::vector<std::string_view> &inputs,
+                                            std::vector<std::vector<int>> *ids) const {
+  if (!engine_) return status();
+  if (!ids) return Internal("output container is null");  // CHECK_OR_RETURN_STATUS_STL
+  ids->clear();
+  std::string bytes;
+  std::vector<uint64_t> offs;
+  Pack(inputs, &bytes, &offs);
+  const int32_t *out;
+  const uint64_t *oo;
+  const auto st = EncodePacked(bytes.data(), offs.data(), inputs.size(), &out, &oo);
+  if (!st.ok()) return st;
+  ids->resize(inputs.size());
+  const int bos = PieceToId(impl_->model.bos_piece), eos = PieceToId(impl_->model.eos_piece);
+  for (size_t i = 0; i < inputs.size(); ++i) {
+    auto &v = (*ids)[i];
+    v.assign(out + oo[i], out + oo[i + 1]);
+    for (const auto o : extra_) {  // ApplyExtraOptions, sentencepiece_processor.cc:1019-1064
+      if (o == REVERSE) std::reverse(v.begin(), v.end());
+      else if (o == EOS) v.push_back(eos);
+      else if (o == BOS) v.insert(v.begin(), bos);
+    }
+  }
+  return util::OkStatus();
+}
+
+util::Status SentencePieceProcessor::Encode(const std::vector<std::string_view> &inputs,
+                                            std::vector<std::vector<std::string>> *pieces) const {
+  if (!engine_) return status();
+  if (!pieces) return Internal("output container is null");
+  pieces->clear();
+  std::string bytes;
+  std::vector<uint64_t> offs;
+  Pack(inputs, &bytes, &offs);
+  const int32_t *ids;
+  const uint32_t *tok_end, *n2o;
+  const uint64_t *ido, *no;
+  const char *norm;
+  const int rc = spm_encode_spans(engine_, bytes.data(), offs.data(), inputs.size(), &ids, &tok_end, &ido, &norm, &no, &n2o);
+  if (rc) return FromEngine(engine_, rc);
+  pieces->resize(inputs.size());
+  const int bos = PieceToId(impl_->model.bos_piece), eos = PieceToId(impl_->model.eos_piece);
+  std::vector<int> pid;
+  for (size_t i = 0; i < inputs.size(); ++i) {
+    auto &v = (*pieces)[i];
+    pid.clear();
+    uint32_t begin = 0;
+    for (uint64_t k = ido[i]; k < ido[i + 1]; ++k) {
+      // unknown pieces keep their normalized surface (sentencepiece_processor.cc:609-621)
+      if (ids[k] == unk_id_) v.emplace_back(norm + no[i] + begin, tok_end[k] - begin);
+      else v.push_back(impl_->pieces[ids[k]]);
+      pid.push_back(ids[k]);
+      begin = tok_end[k];
+    }
+    for (const auto o : extra_) {  // ApplyExtraOptions, sentencepiece_processor.cc:1019-1064
+      if (o == REVERSE) { std::reverse(v.begin(), v.end()); std::reverse(pid.begin(), pid.end()); }
+      else if (o == EOS) { v.push_back(impl_->model.eos_piece); pid.push_back(eos); }
+      else if (o == BOS) { v.insert(v.begin(), impl_->model.bos_piece); pid.insert(pid.begin(), bos); }
+      else if (o == UNK_PIECE)
+        for (size_t k = 0; k < v.size(); ++k)
+          if (pid[k] == unk_id_) v[k] = impl_->model.unk_piece;
+    }
+  }
+  return util::OkStatus();
+}
+
+util::Status SentencePieceProcessor::Encode(std::string_view input, std::vector<int> *ids) const {
+  if (!engine_) return status();
+  if (!ids) return Internal("output container is null");
+  std::vector<std::vector<int>> out;
+  const auto st = Encode(std::vector<std::string_view>{input}, &out);
+  if (!st.ok()) return st;
+  *ids = std::move(out[0]);
+  return util::OkStatus();
+}
+
+util::Status SentencePieceProcessor::Encode(std::string_view input, std::vector<std::string> *pieces) const {
+  if (!engine_) return status();
+  if (!pieces) return Internal("output container is null");
+  std::vector<std::vector<std::string>> out;
+  const auto st = Encode(std::vector<std::string_view>{input}, &out);
+  if (!st.ok()) return st;
+  *pieces = std::move(out[0]);
+  return util::OkStatus();
+}
+
+// the value-returning forms swallow errors (macro at sentencepiece_processor.h:432-436)
+std::vector<std::string> SentencePieceProcessor::EncodeAsPieces(std::string_view input) const {
+  std::vector<std::string> out;
+  Encode(input, &out).IgnoreError();
+  return out;
+}
+std::vector<int> SentencePieceProcessor::EncodeAsIds(std::string_view input) const {
+  std::vector<int> out;
+  Encode(input, &out).IgnoreError();
+  return out;
+}
+
+}  // namespace sentencepiece

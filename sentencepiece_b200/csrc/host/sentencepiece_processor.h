@@ -1,0 +1,99 @@
+// host/sentencepiece_processor.h -- C++ host layer over the C ABI (include/spm_b200.h).
+//
+// Keeps the reference's public encode surface for this path -- class name, namespace,
+// method names, argument meaning and error behaviour of
+// /root/reference/src/sentencepiece_processor.h:238-460 (Load :245,
+// LoadFromSerializedProto :261, SetEncodeExtraOptions :267, SetVocabulary :276,
+// Encode(pieces) :295, Encode(ids) :299, EncodeAsPieces :453, EncodeAsIds :458) --
+// so a caller such as spm_encode compiles against it unchanged, and adds the batch
+// overloads that a GPU needs.  Single-sentence calls are batches of one.
+// Only the encode path is here: training, decoding, n-best/sampling stay the reference's.
+#ifndef SPM_B200_HOST_SENTENCEPIECE_PROCESSOR_H_
+#define SPM_B200_HOST_SENTENCEPIECE_PROCESSOR_H_
+
+#include <cstdint>
+#include <memory>
+#include <string>
+#include <string_view>
+#include <vector>
+
+struct spm_engine;
+
+namespace sentencepiece {
+namespace util {
+
+enum class StatusCode : int { kOk = 0, kNotFound = 5, kInternal = 13 };
+
+// Value-type status, ok() <=> no error (reference: sentencepiece_processor.h:54-76).
+class Status {
+ public:
+  Status() = default;
+  Status(StatusCode code, std::string msg) : code_(code), msg_(std::move(msg)) {}
+  bool ok() const { return code_ == StatusCode::kOk; }
+  StatusCode code() const { return code_; }
+  const std::string &message() const { return msg_; }
+  std::string ToString() const { return ok() ? "OK" : msg_; }
+  void IgnoreError() const {}
+
+ private:
+  StatusCode code_ = StatusCode::kOk;
+  std::string msg_;
+};
+inline Status OkStatus() { return Status(); }
+
+}  // namespace util
+
+class SentencePieceProcessor {
+ public:
+  SentencePieceProcessor();
+  ~SentencePieceProcessor();
+  SentencePieceProcessor(const SentencePieceProcessor &) = delete;
+  SentencePieceProcessor &operator=(const SentencePieceProcessor &) = delete;
+
+  // `device`: CUDA ordinal (one engine per GPU).  Set before Load.
+  void SetDevice(int device) { device_ = device; }
+
+  util::Status Load(std::string_view filename);
+  util::Status LoadFromSerializedProto(std::string_view serialized);
+  util::Status status() const;
+
+  // "bos", "eos", "reverse", "unk"/"unk_piece", colon separated (sentencepiece_processor.cc:1067-1101)
+  util::Status SetEncodeExtraOptions(std::string_view extra_option);
+  util::Status SetVocabulary(const std::vector<std::string_view> &valid_vocab);
+  util::Status ResetVocabulary();
+
+  // ---- single sentence (reference signatures) ----
+  util::Status Encode(std::string_view input, std::vector<std::string> *pieces) const;
+  util::Status Encode(std::string_view input, std::vector<int> *ids) const;
+  std::vector<std::string> EncodeAsPieces(std::string_view input) const;
+  std::vector<int> EncodeAsIds(std::string_view input) const;
+
+  // ---- batch (what the reference's Python layer does with a thread pool,
+  //      python/src/sentencepiece/sentencepiece.i:245-267) ----
+  util::Status Encode(const std::vector<std::string_view> &inputs, std::vector<std::vector<int>> *ids) const;
+  util::Status Encode(const std::vector<std::string_view> &inputs, std::vector<std::vector<std::string>> *pieces) const;
+  // zero-copy form: packed input, packed output owned by the engine until the next call
+  util::Status EncodePacked(const char *bytes, const uint64_t *offsets, size_t n, const int32_t **ids,
+                            const uint64_t **id_offsets) const;
+
+  // ---- vocabulary accessors used by callers of the encode path ----
+  int GetPieceSize() const;
+  int PieceToId(std::string_view piece) const;
+  const std::string &IdToPiece(int id) const;
+  bool IsUnknown(int id) const { return id == unk_id_; }
+  int unk_id() const { return unk_id_; }
+  int bos_id() const;
+  int eos_id() const;
+
+ private:
+  struct Impl;
+  enum ExtraOption { REVERSE, BOS, EOS, UNK_PIECE };
+  std::unique_ptr<Impl> impl_;
+  spm_engine *engine_ = nullptr;
+  int device_ = 0;
+  int unk_id_ = -1;
+  std::vector<ExtraOption> extra_;
+};
+
+}  // namespace sentencepiece
+#endif
