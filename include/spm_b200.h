@@ -147,8 +147,11 @@ typedef struct {
 } spm_engine_info;
 int spm_engine_get_info(const spm_engine *e, spm_engine_info *info);
 
-/* Tuning knobs (benchmark use): tile width (lanes per sentence: 4,8,16,32) and
- * per-sentence shared-memory capacity in normalized bytes.  0 keeps the default. */
+/* Tuning knobs (benchmark use).  lanes_per_sentence selects the unigram kernel: 1 = one sentence
+ * per lane (default), 32 = one sentence per warp with the Viterbi window in registers,
+ * 4/8/16 (and 64 = 32 lanes) = the general tile kernel; smem_norm_cap = per-sentence
+ * shared-memory capacity in normalized bytes; ctas_per_sm >= 32 is read as threads per CTA.
+ * 0 keeps the current value. */
 int spm_engine_set_tuning(spm_engine *e, int lanes_per_sentence, int smem_norm_cap, int ctas_per_sm);
 
 enum spm_error {

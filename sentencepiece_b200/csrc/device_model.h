@@ -17,6 +17,7 @@ enum : uint32_t {
   kFlagHasCharsmap = 1u << 6,
   kFlagBpeWordSplit = 1u << 7,     // no piece has U+2581 past byte 0 (SURVEY 7 "exact decomposition")
   kFlagHasUnused = 1u << 8,        // some piece is currently UNUSED (SetVocabulary)
+  kFlagRegularScores = 1u << 9,    // every piece score is 0 or has 2^-10 <= |score| <= 2^10 (exact float fold)
 };
 
 constexpr uint32_t kValUserDefined = 0xFFFFFFFEu;  // match-buffer marker: USER_DEFINED piece

@@ -25,6 +25,7 @@
 #include "bpe_kernel.cuh"
 #include "device_model.h"
 #include "kernels.cuh"
+#include "lane_kernel.cuh"
 #include "model_reader.h"
 #include "trie_builder.h"
 #include "unigram_warp.cuh"
@@ -134,13 +135,14 @@ struct spm_engine {
   KModel km{};
 
   // tuning
-  int G = 32;
-  int threads = 768;
+  int G = 1;  // 1: lane kernel (sentence per lane); 32: warp kernel; 4/8/16: tile kernel; 64: tile kernel, 32 lanes
+  int threads = 512;
   uint32_t ncap = 256;
+  uint32_t lane_cap = 512;  // normalized-byte capacity per sentence of the lane kernel's slabs
   int ctas_per_sm = 1;
 
   // per-call buffers (grow only)
-  DevBuf<uint8_t> d_bytes, d_tmp_norm, d_norm, d_long_scratch;
+  DevBuf<uint8_t> d_bytes, d_tmp_norm, d_norm, d_long_scratch, d_lane_slabs;
   DevBuf<uint64_t> d_offsets;
   DevBuf<int32_t> d_tmp_ids, d_ids;
   DevBuf<uint32_t> d_tmp_tok_end, d_tok_end, d_tmp_n2o, d_n2o, d_sent_count, d_norm_len, d_deferred, d_long_list, d_ctrl32;
@@ -368,6 +370,14 @@ int spm_engine::build_tables() {
              (charsmap_units ? kFlagHasCharsmap : 0) | (bpe_word_split ? kFlagBpeWordSplit : 0);
   for (uint8_t t : m.types)
     if (t == SPM_UNUSED) km.flags |= kFlagHasUnused;
+  {
+    bool regular = true;
+    for (const TrieKey &k : keys) {
+      const float a = std::fabs(k.score);
+      if (!(k.score == 0.f || (a >= 0.0009765625f && a <= 1024.f))) regular = false;
+    }
+    if (regular) km.flags |= kFlagRegularScores;
+  }
   return SPM_OK;
 }
 
@@ -434,6 +444,8 @@ int spm_engine::configure_kernel_attrs() {
   CUDA_TRY(set_smem(encode_unigram_kernel<32, true>, mx));
   CUDA_TRY(set_smem(encode_unigram_long_kernel<false>, mx));
   CUDA_TRY(set_smem(encode_unigram_long_kernel<true>, mx));
+  CUDA_TRY(set_smem(encode_unigram_lane_kernel<32>, mx));
+  CUDA_TRY(set_smem(encode_unigram_lane_kernel<64>, mx));
   CUDA_TRY(set_smem(encode_unigram_warp_kernel<512>, mx));
   CUDA_TRY(set_smem(encode_unigram_warp_kernel<1024>, mx));
   CUDA_TRY(set_smem(encode_bpe_kernel<false>, mx));
@@ -452,13 +464,16 @@ int spm_engine::run_device(const uint8_t *d_bytes_base, const uint64_t *d_offs, 
   last_deferred = 0;
   const uint32_t n32 = static_cast<uint32_t>(n);
   const bool bpe = model.model_type == SPM_BPE;
-  const int useG = bpe ? 32 : ((spans && G != 32) ? 8 : G);
+  const int tileG = (G == 4 || G == 8 || G == 16) ? G : 32;
+  const int useG = bpe ? 32 : ((spans && tileG != 32) ? 8 : tileG);
   const int tile_threads = std::min(threads, 512);
   const uint32_t K = km.match_slots;
   LaunchGeom geom = plan_geometry(*this, spans, useG, tile_threads, ncap, K);
   // fast unigram path: warp per sentence, register-resident Viterbi window
-  const bool warp_path = !bpe && !spans && trie.max_key_len <= 32 && G == 32 && !getenv("SPM_B200_TILE_KERNEL");
+  const bool lane_path = !bpe && !spans && trie.max_key_len <= 63 && G == 1;
+  const bool warp_path = !bpe && !spans && trie.max_key_len <= 32 && G == 32;
   const int launch_threads = warp_path ? threads : tile_threads;
+  const uint32_t laneR = trie.max_key_len <= 31 ? 32 : 64;
   if (bpe || warp_path) {
     // these kernels own a warp per sentence and their own scratch layout
     geom.tiles = launch_threads / 32;
@@ -469,6 +484,19 @@ int spm_engine::run_device(const uint8_t *d_bytes_base, const uint64_t *d_offs, 
     geom.hot_val = static_cast<uint32_t>(std::min<size_t>(km.trie_units, (hot - static_cast<size_t>(geom.hot_link) * 4) / 4)) & ~3u;
     geom.smem_bytes = static_cast<uint32_t>(16 + static_cast<size_t>(geom.hot_link + geom.hot_val) * 4 +
                                             static_cast<size_t>(geom.tiles) * geom.tile_bytes);
+  }
+  if (lane_path) {
+    geom.tiles = threads / 32;
+    geom.tile_bytes = laneR * 32 * 8;
+    const size_t fixed = 16 + kLaneTableBytes + static_cast<size_t>(geom.tiles) * geom.tile_bytes + 128;
+    size_t hot = smem_optin > fixed ? smem_optin - fixed : 0;
+    if (const char *lim = getenv("SPM_B200_HOT_LIMIT")) hot = std::min<size_t>(hot, strtoull(lim, nullptr, 10));
+    geom.hot_link = static_cast<uint32_t>(std::min<size_t>(km.trie_units, (hot * 3 / 4) / 4)) & ~3u;
+    geom.hot_val = static_cast<uint32_t>(std::min<size_t>(km.trie_units, (hot - static_cast<size_t>(geom.hot_link) * 4) / 4)) & ~3u;
+    geom.smem_bytes = static_cast<uint32_t>(16 + kLaneTableBytes + static_cast<size_t>(geom.hot_link + geom.hot_val) * 4 +
+                                            static_cast<size_t>(geom.tiles) * geom.tile_bytes);
+    const size_t warps_total = static_cast<size_t>(sm_count) * ctas_per_sm * geom.tiles;
+    CUDA_TRY(d_lane_slabs.ensure(warps_total * lane_slab_bytes(lane_cap) + 256));
   }
   if (geom.smem_bytes > smem_optin) { set_error("shared-memory geometry does not fit; lower smem_norm_cap"); return SPM_ERR_ARG; }
   KModel M = km;
@@ -526,6 +554,9 @@ int spm_engine::run_device(const uint8_t *d_bytes_base, const uint64_t *d_offs, 
     if (bpe) {
       if (spans) encode_bpe_kernel<true><<<grid, tile_threads, geom.smem_bytes, st>>>(M, B);
       else encode_bpe_kernel<false><<<grid, tile_threads, geom.smem_bytes, st>>>(M, B);
+    } else if (lane_path) {
+      if (laneR == 32) encode_unigram_lane_kernel<32><<<grid, threads, geom.smem_bytes, st>>>(M, B, d_lane_slabs.p, lane_cap);
+      else encode_unigram_lane_kernel<64><<<grid, threads, geom.smem_bytes, st>>>(M, B, d_lane_slabs.p, lane_cap);
     } else if (warp_path) {
       if (threads <= 512) encode_unigram_warp_kernel<512><<<grid, threads, geom.smem_bytes, st>>>(M, B);
       else encode_unigram_warp_kernel<1024><<<grid, threads, geom.smem_bytes, st>>>(M, B);
@@ -751,6 +782,7 @@ void spm_engine_destroy(spm_engine *e) {
   e->d_ctrl32.release(); e->d_sent_start.release(); e->d_norm_start.release(); e->d_id_offsets.release();
   e->d_norm_offsets.release(); e->d_n2o_offsets.release(); e->d_block_sums.release(); e->d_ctrl64.release();
   e->d_long_off.release();
+  e->d_lane_slabs.release();
   e->h_ids.release(); e->h_tok_end.release(); e->h_n2o.release(); e->h_ctrl32.release(); e->h_deferred.release();
   e->h_id_offsets.release(); e->h_norm_offsets.release(); e->h_ctrl64.release(); e->h_norm.release();
   for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
@@ -806,7 +838,7 @@ int spm_engine_set_tuning(spm_engine *e, int lanes, int cap, int ctas) {
   if (!e) return SPM_ERR_ARG;
   std::lock_guard<std::mutex> lk(e->mu);
   if (lanes) {
-    if (lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32) { e->set_error("lanes_per_sentence must be 4, 8, 16 or 32"); return SPM_ERR_ARG; }
+    if (lanes != 1 && lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32 && lanes != 64) { e->set_error("lanes_per_sentence must be 1, 4, 8, 16, 32 or 64"); return SPM_ERR_ARG; }
     e->G = lanes;
   }
   if (cap) {

@@ -1,0 +1,535 @@
+// lane_kernel.cuh -- unigram fast path: one sentence per LANE (32 sentences per warp).
+//
+// Measured motivation (profiles/r01_v1_*): with one sentence per warp the kernel is
+// instruction-issue bound and ~65 % of the issued instructions are the ORDERED fold of
+// Viterbi edges, where 31 of 32 lanes repeat the same scalar work.  The reference
+// algorithm (src/unigram_model.cc:889-1020) is a short sequential state machine per
+// sentence; running it one sentence per lane makes every instruction do 32 sentences'
+// worth of work (~4x fewer issued instructions per sentence, profiles/r01_v2_*).
+//
+// Per lane, per sentence:
+//   K1  Normalizer::Normalize / NormalizePrefix, sequentially (src/normalizer.cc:71-253).
+//       Input bytes stream through a 32-byte register window (aligned 16-byte loads, next
+//       chunk prefetched); the ASCII fast-path tables of the charsmap sit in shared
+//       memory; normalized text goes to a per-lane slab in HBM/L2 with words interleaved
+//       by lane.
+//   K2  EncodeOptimized as a flat state machine: each loop trip is ONE trie transition
+//       for every lane (hot trie prefix in shared memory, rest L2).  The text is read
+//       through a 16-byte register window anchored at the current start (next word
+//       prefetched at each start transition).  best_path_ends_at[] only ever needs the
+//       positions [s, s + max_piece_len], so it lives in a per-lane RING in shared memory
+//       laid out [slot][lane] (bank == lane: conflict free).  When a position becomes a
+//       start its final back-pointer is appended to a per-lane LOG (entry t of every lane
+//       shares a cache line), so the back-trace is a coalesced backward scan.
+//   K4  back-trace + id path of PopulateSentencePieceText: two backward scans of the log
+//       (count, then write) around one warp-aggregated claim of output space.
+// Exactly the reference's relaxation order and mixed float/double comparison.
+#ifndef SPM_B200_LANE_KERNEL_CUH_
+#define SPM_B200_LANE_KERNEL_CUH_
+
+#include "kernels.cuh"
+
+namespace spm_b200 {
+
+constexpr uint32_t kLaneUnk = 0x3FFFFFu;  // 22-bit trie-unit field: UNK piece
+
+// slab geometry: per warp [text words: cap/4 + 4][32] u32, then [log: cap + 4][32] u32
+__host__ __device__ inline unsigned long long lane_slab_bytes(uint32_t cap) {
+  return (static_cast<unsigned long long>(cap / 4 + 4) + (cap + 4)) * 32ull * 4ull;
+}
+// shared memory for the normalizer's fast-path tables
+constexpr uint32_t kLaneTableBytes = 32 + 4096 + 512;  // cm_lead[8] + cm_pair[1024] + cm_solo[128]
+
+struct LaneCtx {
+  uint32_t *text_w;  // + word*32 (already offset by lane)
+  uint32_t *log;     // + t*32    (already offset by lane)
+  float *rs;         // ring scores, + slot*32 (already offset by lane)
+  uint32_t *rb;      // ring back-pointers (plen<<24 | unit), 0 = unset
+  const uint32_t *s_lead, *s_pair;
+  const int32_t *s_solo;
+};
+
+// Sequential byte stream over a lane's input: 16-byte aligned chunks (next chunk prefetched)
+// feed a 64-bit shift register that always exposes the next >= 4 bytes.
+struct ByteStream {
+  const uint4 *cp;      // chunk that `nxt` was loaded from, + 1
+  const uint4 *cend;    // first chunk past the sentence
+  uint4 cur, nxt;
+  uint32_t wi;          // next word of `cur` to feed (0..3)
+  unsigned long long win;
+  uint32_t have;        // valid bytes in win
+  __device__ __forceinline__ uint32_t next_word() {
+    const uint32_t w = wi == 0 ? cur.x : (wi == 1 ? cur.y : (wi == 2 ? cur.z : cur.w));
+    if (++wi == 4) {
+      wi = 0;
+      cur = nxt;
+      nxt = cp < cend ? __ldg(cp) : make_uint4(0, 0, 0, 0);
+      ++cp;
+    }
+    return w;
+  }
+  __device__ __forceinline__ void init(const uint8_t *p, const uint8_t *hi) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint4 *c0 = reinterpret_cast<const uint4 *>(a & ~static_cast<uintptr_t>(15));
+    cend = reinterpret_cast<const uint4 *>((reinterpret_cast<uintptr_t>(hi) + 15) & ~static_cast<uintptr_t>(15));
+    cur = __ldg(c0);
+    nxt = c0 + 1 < cend ? __ldg(c0 + 1) : make_uint4(0, 0, 0, 0);
+    cp = c0 + 2;
+    wi = static_cast<uint32_t>((a & 15) >> 2);
+    const uint32_t mis = static_cast<uint32_t>(a & 3);
+    const uint32_t w = next_word();
+    win = static_cast<unsigned long long>(w >> (8 * mis));
+    have = 4 - mis;
+    win |= static_cast<unsigned long long>(next_word()) << (8 * have);
+    have += 4;
+  }
+  __device__ __forceinline__ uint32_t peek(uint32_t i) const { return static_cast<uint32_t>(win >> (8 * i)) & 0xFFu; }
+  __device__ __forceinline__ void consume(uint32_t c) {  // c <= 4
+    win >>= 8 * c;
+    have -= c;
+    if (have <= 4) {
+      win |= static_cast<unsigned long long>(next_word()) << (8 * have);
+      have += 4;
+    }
+  }
+};
+
+// Sequential normalizer for one lane.  Returns the normalized length, or 0xFFFFFFFF if
+// it exceeds `cap` (the caller defers the sentence).
+__device__ __forceinline__ uint32_t lane_normalize(const KModel &M, const uint8_t *in, uint32_t len, const LaneCtx &c,
+                                                   uint32_t cap) {
+  const bool rm = M.flags & kFlagRemoveExtraWs;
+  const bool esc = M.flags & kFlagEscapeWs;
+  const bool suffix = M.flags & kFlagWsSuffix;
+  const bool addp = M.flags & kFlagAddDummyPrefix;
+  const bool has_user = M.flags & kFlagHasUserSymbols;
+  const bool has_cm = M.flags & kFlagHasCharsmap;
+  if (len == 0) return 0;
+  ByteStream S;
+  S.init(in, in + len);
+  uint32_t out = 0;  // normalized bytes produced
+  uint32_t acc = 0;  // partial word
+  bool overflow = false;
+  auto put = [&](uint32_t ch) {
+    acc |= ch << ((out & 3u) * 8u);
+    if ((out & 3u) == 3u) {
+      if (out < cap) c.text_w[static_cast<size_t>(out >> 2) * 32] = acc; else overflow = true;
+      acc = 0;
+    }
+    ++out;
+  };
+  auto put_ws = [&]() {
+    if (esc) { put(0xE2); put(0x96); put(0x81); } else { put(' '); }
+  };
+  uint32_t pos = 0;
+  bool is_prev_space = rm;  // normalizer.cc:130
+  bool started = !rm;       // the heading-space loop (:86-95) is over
+  if (started && addp && !suffix) put_ws();  // dummy prefix (:128); with the heading loop it is emitted when that ends
+  // One chunk of NormalizePrefix (normalizer.cc:195-253) + the emit logic of Normalize (:131-163)
+  while (pos < len) {
+    const uint32_t rem = len - pos;
+    const uint32_t b = S.peek(0);
+    uint32_t consumed = 1;
+    // replacement string: kind + (pointer | inline bytes)
+    uint32_t kind = kChunkChar, spl = 1;
+    const uint8_t *sp = nullptr;
+    bool generic = false;
+    if (has_user) {
+      const uint32_t ul = user_longest(M, in + pos, rem);
+      if (ul) { consumed = ul; spl = ul; kind = kChunkVerbatim; sp = in + pos; generic = true; }
+    }
+    if (!generic) {
+      uint32_t longest = 0, value = 0;
+      if (has_cm && ((c.s_lead[b >> 5] >> (b & 31u)) & 1u)) {
+        if (b < 0x80u) {
+          bool cont = false;
+          if (rem > 1) {
+            const uint32_t c2 = S.peek(1);
+            cont = (c.s_pair[(b * 256u + c2) >> 5] >> (c2 & 31u)) & 1u;
+          }
+          if (cont) longest = charsmap_longest(M, in + pos, rem, &value);
+          else {
+            const int32_t so = c.s_solo[b];
+            if (so >= 0) { longest = 1; value = static_cast<uint32_t>(so); }
+          }
+        } else {
+          longest = charsmap_longest(M, in + pos, rem, &value);
+        }
+      }
+      if (longest) {
+        consumed = longest; kind = kChunkTarget; sp = M.cm_targets + value; generic = true;
+        spl = 0;
+        while (__ldg(sp + spl) != 0) ++spl;
+      } else if (b < 0x80u) {
+        // ---- fast path: one ASCII byte that is not a rule ----
+        if (!started) {
+          if (b == ' ') { ++pos; S.consume(1); continue; }  // heading space
+          started = true;
+          if (addp && !suffix) put_ws();
+        }
+        if (b == ' ') {
+          if (!is_prev_space) { put_ws(); is_prev_space = rm; }
+        } else {
+          put(b);
+          is_prev_space = false;
+        }
+        ++pos;
+        S.consume(1);
+        continue;
+      } else {
+        // DecodeUTF8 / IsValidDecodeUTF8 (util.cc:51-84) on the stream's look-ahead bytes
+        uint32_t l = 0;
+        const uint32_t b1 = S.peek(1), b2 = S.peek(2), b3 = S.peek(3);
+        if (rem >= 2 && (b & 0xE0u) == 0xC0u) {
+          if (is_trail(b1) && (((b & 0x1Fu) << 6) | (b1 & 0x3Fu)) >= 0x80u) l = 2;
+        } else if (rem >= 3 && (b & 0xF0u) == 0xE0u) {
+          const uint32_t cp = ((b & 0x0Fu) << 12) | ((b1 & 0x3Fu) << 6) | (b2 & 0x3Fu);
+          if (is_trail(b1) && is_trail(b2) && cp >= 0x800u && (cp < 0xD800u || cp >= 0xE000u)) l = 3;
+        } else if (rem >= 4 && (b & 0xF8u) == 0xF0u) {
+          const uint32_t cp = ((b & 0x07u) << 18) | ((b1 & 0x3Fu) << 12) | ((b2 & 0x3Fu) << 6) | (b3 & 0x3Fu);
+          if (is_trail(b1) && is_trail(b2) && is_trail(b3) && cp >= 0x10000u && cp <= 0x10FFFFu) l = 4;
+        }
+        if (!started) { started = true; if (addp && !suffix) put_ws(); }
+        if (l) {  // a valid multi-byte character: never a space
+          put(b); put(b1);
+          if (l > 2) put(b2);
+          if (l > 3) put(b3);
+          consumed = l;
+        } else {  // malformed: one byte -> U+FFFD (normalizer.cc:231-244)
+          put(0xEF); put(0xBF); put(0xBD);
+          consumed = 1;
+        }
+        is_prev_space = false;
+        pos += consumed;
+        S.consume(consumed);
+        continue;
+      }
+    }
+    // ---- generic path: rule targets and verbatim user symbols ----
+    if (!started) {
+      if (spl == 1 && __ldg(sp) == ' ') {  // a chunk that is exactly " " during the heading loop
+        pos += consumed;
+        if (consumed <= 4) S.consume(consumed); else S.init(in + pos, in + len);
+        continue;
+      }
+      started = true;
+      if (addp && !suffix) put_ws();
+    }
+    {
+      uint32_t i0 = 0;
+      while (is_prev_space && i0 < spl && __ldg(sp + i0) == ' ') ++i0;  // :137-138
+      if (i0 < spl) {
+        uint32_t last = 0;
+        for (uint32_t i = i0; i < spl; ++i) {
+          last = __ldg(sp + i);
+          if (last == ' ' && esc) { put(0xE2); put(0x96); put(0x81); } else put(last);
+        }
+        is_prev_space = last == ' ';
+      }
+      if (!rm) is_prev_space = false;
+    }
+    pos += consumed;
+    if (consumed <= 4) S.consume(consumed); else S.init(in + pos, in + len);
+  }
+  if (!started) return 0;  // all chars are whitespace (:97-100)
+  if (overflow || out > cap) return 0xFFFFFFFFu;
+  // flush the partial word, then strip trailing spaces on the escaped output (:166-176)
+  c.text_w[static_cast<size_t>(out >> 2) * 32] = acc;
+  if (rm) {
+    auto byte_at = [&](uint32_t k) -> uint32_t {
+      return (c.text_w[static_cast<size_t>(k >> 2) * 32] >> ((k & 3u) * 8u)) & 0xFFu;
+    };
+    if (esc) {
+      while (out >= 3 && byte_at(out - 3) == 0xE2 && byte_at(out - 2) == 0x96 && byte_at(out - 1) == 0x81) out -= 3;
+    } else {
+      while (out >= 1 && byte_at(out - 1) == ' ') out -= 1;
+    }
+  }
+  if (suffix && addp) {  // :179
+    if (out + 3 > cap) return 0xFFFFFFFFu;
+    acc = (out & 3u) ? (c.text_w[static_cast<size_t>(out >> 2) * 32] & ((1u << ((out & 3u) * 8u)) - 1u)) : 0u;
+    put_ws();
+    c.text_w[static_cast<size_t>(out >> 2) * 32] = acc;
+  }
+  return out;
+}
+
+template <int R>
+__global__ void __launch_bounds__(1024, 1) encode_unigram_lane_kernel(const KModel M, const KBatch B, uint8_t *slabs,
+                                                                       uint32_t cap) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t *mbar = reinterpret_cast<uint64_t *>(smem);
+  uint32_t *s_link = reinterpret_cast<uint32_t *>(smem + 16);
+  uint32_t *s_val = s_link + M.hot_link;
+  uint32_t *s_tab = s_val + M.hot_val;
+  uint8_t *rings = reinterpret_cast<uint8_t *>(s_tab) + kLaneTableBytes;
+  // normalizer fast-path tables -> shared memory (L1 is tiny under this carve-out)
+  for (uint32_t i = threadIdx.x; i < kLaneTableBytes / 4; i += blockDim.x) {
+    uint32_t v;
+    if (i < 8) v = M.cm_lead[i];
+    else if (i < 8 + 1024) v = M.cm_pair[i - 8];
+    else v = static_cast<uint32_t>(M.cm_solo[i - 8 - 1024]);
+    s_tab[i] = v;
+  }
+  stage_hot_trie(M, mbar, s_link, s_val);
+  __syncthreads();
+  const HotTrie H{s_link, s_val, M.trie_link, M.trie_val, M.hot_link, M.hot_val};
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warp_in_cta = threadIdx.x >> 5;
+  const uint32_t warp_global = blockIdx.x * (blockDim.x >> 5) + warp_in_cta;
+  constexpr uint32_t RM = R - 1;
+  LaneCtx c;
+  {
+    uint8_t *ring = rings + static_cast<size_t>(warp_in_cta) * (R * 32 * 8);
+    c.rs = reinterpret_cast<float *>(ring) + lane;
+    c.rb = reinterpret_cast<uint32_t *>(ring + R * 32 * 4) + lane;
+    uint8_t *slab = slabs + static_cast<size_t>(warp_global) * lane_slab_bytes(cap);
+    c.text_w = reinterpret_cast<uint32_t *>(slab) + lane;
+    c.log = reinterpret_cast<uint32_t *>(slab) + static_cast<size_t>(cap / 4 + 4) * 32 + lane;
+    c.s_lead = s_tab;
+    c.s_pair = s_tab + 8;
+    c.s_solo = reinterpret_cast<const int32_t *>(s_tab + 8 + 1024);
+  }
+  const uint32_t root = H.link(0);
+  const bool bf = M.flags & kFlagByteFallback;
+  const bool regular = M.flags & kFlagRegularScores;
+
+  for (;;) {
+    uint32_t first = 0;
+    if (lane == 0) first = atomicAdd(B.work_counter, 32u);
+    first = __shfl_sync(0xFFFFFFFFu, first, 0);
+    if (first >= B.n) break;
+    const uint32_t sent = first + lane;
+    const bool have = sent < B.n;
+    // ---------------- K1 ----------------
+    uint32_t n = 0;
+    bool defer = false;
+    if (have) {
+      const unsigned long long off = B.offsets[sent];
+      const unsigned long long len64 = B.offsets[sent + 1] - off;
+      if (len64 > 4ull * cap) defer = true;
+      else {
+        n = lane_normalize(M, B.bytes + off, static_cast<uint32_t>(len64), c, cap);
+        if (n == 0xFFFFFFFFu) { defer = true; n = 0; }
+      }
+      if (defer) {
+        const uint32_t slot = atomicAdd(B.status, 1u);
+        B.deferred[2 * slot] = sent;
+        B.deferred[2 * slot + 1] = 0;
+      }
+    }
+    __syncwarp();
+    // ---------------- K2: flat state machine, one trie transition per trip ----------------
+    uint32_t s = 0, k = 0, l = root, mblen = 1, nlog = 0;
+    bool has_single = false, done = n == 0;
+    float base = 0.f;
+    bool base_regular = regular;  // base == 0
+    uint32_t aw = 0;              // anchor word of the text window
+    uint32_t t0 = 0, t1 = 0, t2 = 0, t3 = 0;  // text bytes [4*aw, 4*aw+16)
+    auto text_at = [&](uint32_t kk) -> uint32_t {
+      const uint32_t d = kk - 4u * aw;
+      uint32_t w;
+      if (d < 16u) {
+        const uint32_t ws = d >> 2;
+        w = ws == 0 ? t0 : (ws == 1 ? t1 : (ws == 2 ? t2 : t3));
+      } else {
+        w = c.text_w[static_cast<size_t>(kk >> 2) * 32];  // beyond the window: long piece, rare
+      }
+      return (w >> ((kk & 3u) * 8u)) & 0xFFu;
+    };
+    if (!done) {
+      for (uint32_t r = 0; r < static_cast<uint32_t>(R); ++r) c.rb[r * 32] = 0u;  // all positions unset
+      c.rs[0] = 0.f;
+      t0 = c.text_w[0]; t1 = c.text_w[32]; t2 = c.text_w[64]; t3 = c.text_w[96];
+      mblen = one_char_len(t0 & 0xFFu);
+      if (mblen > n) mblen = n;
+    }
+    while (__any_sync(0xFFFFFFFFu, !done)) {
+      if (!done) {
+        bool ok = false;
+        uint32_t v = 0, nl = 0;
+        if (k < n) {
+          const uint32_t ch = text_at(k);
+          v = (l >> kLinkBaseShift) ^ ch;
+          nl = H.link(v);
+          ok = (nl & kLinkLabelMask) == ch;
+        }
+        if (ok) {
+          ++k;
+          l = nl;
+          const uint32_t kind = (nl >> kLinkKindShift) & 3u;
+          if (kind == kKindNormal || kind == kKindUserDefined) {
+            const uint32_t plen = k - s;
+            const uint32_t slot = (k & RM) * 32;
+            const float cur = c.rs[slot];
+            const bool unset = c.rb[slot] == 0u;
+            float ns;
+            bool better;
+            if (kind == kKindNormal && base_regular) {
+              // Exact float formulation of the reference's double comparison (Q1).  With
+              // |score|, |base| in {0} U [2^-10, 2^18) the double sum a + b is exact, so
+              // (float)cand == fl(a + b) and cand > cur  <=>  ns > cur || (ns == cur && err > 0),
+              // err being the exact rounding error of the float add (Knuth two-sum).
+              const float a = __uint_as_float(H.val(v));
+              ns = __fadd_rn(a, base);
+              const float bb = __fsub_rn(ns, a);
+              const float err = __fadd_rn(__fsub_rn(a, __fsub_rn(ns, bb)), __fsub_rn(base, bb));
+              better = unset || ns > cur || (ns == cur && err > 0.f);
+            } else {
+              const double sc = kind == kKindNormal
+                                    ? static_cast<double>(__uint_as_float(H.val(v)))
+                                    : static_cast<double>(__fmul_rn(static_cast<float>(plen), M.max_score)) - 0.1;
+              const double cand = sc + static_cast<double>(base);
+              better = unset || cand > static_cast<double>(cur);
+              ns = static_cast<float>(cand);
+            }
+            if (better) {
+              c.rs[slot] = ns;
+              c.rb[slot] = (plen << 24) | v;
+            }
+            has_single |= plen == mblen;
+          }
+        } else {
+          // the walk from s is over (traverse() == -2, or end of text)
+          if (!has_single) {  // UNK edge, unigram_model.cc:995-1005
+            const uint32_t slot = ((s + mblen) & RM) * 32;
+            const float cand = __fadd_rn(M.unk_score, base);
+            if (c.rb[slot] == 0u || cand > c.rs[slot]) {
+              c.rs[slot] = cand;
+              c.rb[slot] = (mblen << 24) | kLaneUnk;
+            }
+          }
+          // position s leaves the window; only character starts are ever targets, so its
+          // slot is the only one that has to be cleared for position s + R
+          c.rb[(s & RM) * 32] = 0u;
+          s += mblen;
+          const uint32_t slot = (s & RM) * 32;
+          // position s is final: append (plen | previous char length | unit) to the log
+          c.log[static_cast<size_t>(nlog) * 32] = c.rb[slot] | ((mblen - 1u) << 22);
+          ++nlog;
+          if (s >= n) {
+            done = true;
+          } else {
+            base = c.rs[slot];
+            base_regular = regular && (base == 0.f || (fabsf(base) >= 0.0009765625f && fabsf(base) < 262144.f));
+            // slide the text window so that it is anchored at s; prefetch the new tail word
+            const uint32_t naw = s >> 2;
+            if (naw != aw) {
+              if (naw == aw + 1) { t0 = t1; t1 = t2; t2 = t3; t3 = c.text_w[static_cast<size_t>(naw + 3) * 32]; }
+              else {
+                t0 = c.text_w[static_cast<size_t>(naw) * 32]; t1 = c.text_w[static_cast<size_t>(naw + 1) * 32];
+                t2 = c.text_w[static_cast<size_t>(naw + 2) * 32]; t3 = c.text_w[static_cast<size_t>(naw + 3) * 32];
+              }
+              aw = naw;
+            }
+            const uint32_t lead = (t0 >> ((s & 3u) * 8u)) & 0xFFu;
+            mblen = one_char_len(lead);
+            if (mblen > n - s) mblen = n - s;
+            k = s;
+            l = root;
+            has_single = false;
+          }
+        }
+      }
+    }
+    // ---------------- K4: coalesced backward scans of the log ----------------
+    // entry t (t = 0..nlog-1) belongs to the (t+1)-th character boundary p_t; the character
+    // before p_t has (entry>>22 & 3) + 1 bytes, so positions are recovered going backwards.
+    const uint32_t max_log = __reduce_max_sync(0xFFFFFFFFu, nlog);
+    uint32_t count = 0;
+    {
+      uint32_t pos_b = n, want = n;
+      bool prev_unk = false;
+      for (uint32_t tb = (max_log + 3u) & ~3u; tb > 0; tb -= 4) {
+        uint32_t ev[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {  // four independent, coalesced loads per trip
+          const uint32_t t = tb - 1 - j;
+          ev[j] = t < nlog ? c.log[static_cast<size_t>(t) * 32] : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t t = tb - 1 - j;
+          if (t < nlog) {
+            const uint32_t e = ev[j];
+            if (pos_b == want) {
+              const uint32_t plen = e >> 24;
+              const bool isunk = (e & 0x3FFFFFu) == kLaneUnk;
+              if (bf) count += isunk ? plen : 1u;
+              else count += !(isunk && prev_unk);
+              prev_unk = isunk;
+              want -= plen;
+            }
+            pos_b -= ((e >> 22) & 3u) + 1u;
+          }
+        }
+      }
+      if (n && want != 0) { atomicOr(B.status + 1, 1u); count = 0; }
+    }
+    // one claim of output space per warp
+    uint32_t incl = count;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+      if (lane >= static_cast<uint32_t>(d)) incl += t;
+    }
+    const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    unsigned long long pos = 0;
+    if (lane == 0 && total) {
+      pos = atomicAdd(B.cursor, static_cast<unsigned long long>(total));
+      if (pos + total > B.tmp_cap) atomicOr(B.status + 2, 1u);
+    }
+    pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
+    const bool room = pos + total <= B.tmp_cap;
+    pos += incl - count;
+    if (have && !defer) {
+      B.sent_start[sent] = pos;
+      B.sent_count[sent] = room ? count : 0u;
+    }
+    // second backward scan: write ids from the end
+    if (room) {
+      uint32_t pos_b = n, want = n, w = count;
+      bool prev_unk = false;
+      for (uint32_t tb = (max_log + 3u) & ~3u; tb > 0; tb -= 4) {
+        uint32_t ev[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t t = tb - 1 - j;
+          ev[j] = t < nlog ? c.log[static_cast<size_t>(t) * 32] : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+        const uint32_t t = tb - 1 - j;
+        if (t < nlog && w > 0) {
+          const uint32_t e = ev[j];
+          if (pos_b == want) {
+            const uint32_t plen = e >> 24;
+            const uint32_t idx = e & 0x3FFFFFu;
+            const bool isunk = idx == kLaneUnk;
+            if (isunk) {
+              if (bf) {
+                for (uint32_t i = 0; i < plen; ++i) {
+                  const uint32_t kk = want - 1 - i;
+                  const uint32_t ch = (c.text_w[static_cast<size_t>(kk >> 2) * 32] >> ((kk & 3u) * 8u)) & 0xFFu;
+                  B.tmp_ids[pos + (--w)] = __ldg(M.byte_to_id + ch);
+                }
+              } else if (!prev_unk) {
+                B.tmp_ids[pos + (--w)] = M.unk_id;
+              }
+            } else {
+              B.tmp_ids[pos + (--w)] = __ldg(M.trie_id + idx);
+            }
+            prev_unk = isunk;
+            want -= plen;
+          }
+          pos_b -= ((e >> 22) & 3u) + 1u;
+        }
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace spm_b200
+#endif
