@@ -4,6 +4,8 @@
 
 #include <cstdint>
 
+#include <vector_types.h>
+
 namespace spm_b200 {
 
 // flags of KModel::flags
@@ -31,6 +33,7 @@ struct KModel {
   const uint32_t *trie_link;
   const uint32_t *trie_val;
   const int32_t *trie_id;
+  const uint2 *trie_node2;  // {link, child mask} interleaved (lane kernel: one 8-byte load per transition)
   uint32_t trie_units;
   uint32_t hot_link;   // units of trie_link staged into shared memory by each CTA (multiple of 4)
   uint32_t hot_val;    // units of trie_val staged (multiple of 4)

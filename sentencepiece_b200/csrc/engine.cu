@@ -128,7 +128,7 @@ struct spm_engine {
   bool bpe_word_split = false;
 
   // device tables
-  DevBuf<uint32_t> d_link, d_val, d_user_link, d_cm_units, d_cm_lead, d_cm_pair;
+  DevBuf<uint32_t> d_link, d_val, d_user_link, d_cm_units, d_cm_lead, d_cm_pair, d_node2;
   DevBuf<int32_t> d_id, d_cm_solo, d_byte_to_id;
   DevBuf<uint8_t> d_cm_targets, d_types;
   DevBuf<float> d_scores;
@@ -136,7 +136,7 @@ struct spm_engine {
 
   // tuning
   int G = 1;  // 1: lane kernel (sentence per lane); 32: warp kernel; 4/8/16: tile kernel; 64: tile kernel, 32 lanes
-  int threads = 512;
+  int threads = 1024;
   uint32_t ncap = 256;
   uint32_t lane_cap = 512;  // normalized-byte capacity per sentence of the lane kernel's slabs
   int ctas_per_sm = 1;
@@ -161,6 +161,7 @@ struct spm_engine {
   void set_error(const std::string &m) const { err = m; }
   int build_tables();
   int upload_types();
+  int upload_node2();
   int configure_kernel_attrs();
   int run_device(const uint8_t *d_bytes_base, const uint64_t *d_offs, size_t n, uint64_t total_bytes, bool spans,
                  int32_t *user_ids, uint64_t user_ids_cap, unsigned long long *user_id_offsets, uint64_t *total_ids,
@@ -345,6 +346,7 @@ int spm_engine::build_tables() {
   CUDA_TRY(d_scores.upload(m.scores));
   CUDA_TRY(d_types.upload(m.types));
 
+  { const int rc2 = upload_node2(); if (rc2) return rc2; }
   km.trie_link = d_link.p;
   km.trie_val = d_val.p;
   km.trie_id = d_id.p;
@@ -381,6 +383,15 @@ int spm_engine::build_tables() {
   return SPM_OK;
 }
 
+// {link, child mask} pairs for the lane kernel.
+int spm_engine::upload_node2() {
+  std::vector<uint32_t> n2(trie.link.size() * 2);
+  for (size_t u = 0; u < trie.link.size(); ++u) { n2[2 * u] = trie.link[u]; n2[2 * u + 1] = trie.cmask[u]; }
+  CUDA_TRY(d_node2.upload(n2));
+  km.trie_node2 = reinterpret_cast<const uint2 *>(d_node2.p);
+  return SPM_OK;
+}
+
 // Live piece types -> trie link words (kind bits) + types array.
 int spm_engine::upload_types() {
   for (int i = 0; i < model.vocab_size(); ++i) {
@@ -396,7 +407,7 @@ int spm_engine::upload_types() {
   CUDA_TRY(cudaSetDevice(device));
   CUDA_TRY(d_link.upload(trie.link));
   CUDA_TRY(d_types.upload(model.types));
-  return SPM_OK;
+  return upload_node2();
 }
 
 // -------------------------------------------------------------- launches ---
@@ -444,8 +455,7 @@ int spm_engine::configure_kernel_attrs() {
   CUDA_TRY(set_smem(encode_unigram_kernel<32, true>, mx));
   CUDA_TRY(set_smem(encode_unigram_long_kernel<false>, mx));
   CUDA_TRY(set_smem(encode_unigram_long_kernel<true>, mx));
-  CUDA_TRY(set_smem(encode_unigram_lane_kernel<32>, mx));
-  CUDA_TRY(set_smem(encode_unigram_lane_kernel<64>, mx));
+  CUDA_TRY(set_smem(encode_unigram_lane_kernel, mx));
   CUDA_TRY(set_smem(encode_unigram_warp_kernel<512>, mx));
   CUDA_TRY(set_smem(encode_unigram_warp_kernel<1024>, mx));
   CUDA_TRY(set_smem(encode_bpe_kernel<false>, mx));
@@ -470,10 +480,10 @@ int spm_engine::run_device(const uint8_t *d_bytes_base, const uint64_t *d_offs, 
   const uint32_t K = km.match_slots;
   LaunchGeom geom = plan_geometry(*this, spans, useG, tile_threads, ncap, K);
   // fast unigram path: warp per sentence, register-resident Viterbi window
-  const bool lane_path = !bpe && !spans && trie.max_key_len <= 63 && G == 1;
+  const bool lane_path = !bpe && !spans && trie.max_key_len <= 62 && G == 1;
   const bool warp_path = !bpe && !spans && trie.max_key_len <= 32 && G == 32;
   const int launch_threads = warp_path ? threads : tile_threads;
-  const uint32_t laneR = trie.max_key_len <= 31 ? 32 : 64;
+  const uint32_t laneR = trie.max_key_len + 2;  // ring slots: positions [s, s + max piece length]
   if (bpe || warp_path) {
     // these kernels own a warp per sentence and their own scratch layout
     geom.tiles = launch_threads / 32;
@@ -488,13 +498,8 @@ int spm_engine::run_device(const uint8_t *d_bytes_base, const uint64_t *d_offs, 
   if (lane_path) {
     geom.tiles = threads / 32;
     geom.tile_bytes = laneR * 32 * 8;
-    const size_t fixed = 16 + kLaneTableBytes + static_cast<size_t>(geom.tiles) * geom.tile_bytes + 128;
-    size_t hot = smem_optin > fixed ? smem_optin - fixed : 0;
-    if (const char *lim = getenv("SPM_B200_HOT_LIMIT")) hot = std::min<size_t>(hot, strtoull(lim, nullptr, 10));
-    geom.hot_link = static_cast<uint32_t>(std::min<size_t>(km.trie_units, (hot * 3 / 4) / 4)) & ~3u;
-    geom.hot_val = static_cast<uint32_t>(std::min<size_t>(km.trie_units, (hot - static_cast<size_t>(geom.hot_link) * 4) / 4)) & ~3u;
-    geom.smem_bytes = static_cast<uint32_t>(16 + kLaneTableBytes + static_cast<size_t>(geom.hot_link + geom.hot_val) * 4 +
-                                            static_cast<size_t>(geom.tiles) * geom.tile_bytes);
+    geom.hot_link = geom.hot_val = 0;  // the lane kernel reads the trie through L1: rings get the shared memory
+    geom.smem_bytes = static_cast<uint32_t>(kLaneTableBytes + static_cast<size_t>(geom.tiles) * geom.tile_bytes);
     const size_t warps_total = static_cast<size_t>(sm_count) * ctas_per_sm * geom.tiles;
     CUDA_TRY(d_lane_slabs.ensure(warps_total * lane_slab_bytes(lane_cap) + 256));
   }
@@ -555,8 +560,7 @@ int spm_engine::run_device(const uint8_t *d_bytes_base, const uint64_t *d_offs, 
       if (spans) encode_bpe_kernel<true><<<grid, tile_threads, geom.smem_bytes, st>>>(M, B);
       else encode_bpe_kernel<false><<<grid, tile_threads, geom.smem_bytes, st>>>(M, B);
     } else if (lane_path) {
-      if (laneR == 32) encode_unigram_lane_kernel<32><<<grid, threads, geom.smem_bytes, st>>>(M, B, d_lane_slabs.p, lane_cap);
-      else encode_unigram_lane_kernel<64><<<grid, threads, geom.smem_bytes, st>>>(M, B, d_lane_slabs.p, lane_cap);
+      encode_unigram_lane_kernel<<<grid, threads, geom.smem_bytes, st>>>(M, B, d_lane_slabs.p, lane_cap, laneR);
     } else if (warp_path) {
       if (threads <= 512) encode_unigram_warp_kernel<512><<<grid, threads, geom.smem_bytes, st>>>(M, B);
       else encode_unigram_warp_kernel<1024><<<grid, threads, geom.smem_bytes, st>>>(M, B);
@@ -783,6 +787,7 @@ void spm_engine_destroy(spm_engine *e) {
   e->d_norm_offsets.release(); e->d_n2o_offsets.release(); e->d_block_sums.release(); e->d_ctrl64.release();
   e->d_long_off.release();
   e->d_lane_slabs.release();
+  e->d_node2.release();
   e->h_ids.release(); e->h_tok_end.release(); e->h_n2o.release(); e->h_ctrl32.release(); e->h_deferred.release();
   e->h_id_offsets.release(); e->h_norm_offsets.release(); e->h_ctrl64.release(); e->h_norm.release();
   for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);

@@ -254,16 +254,12 @@ __device__ __forceinline__ uint32_t lane_normalize(const KModel &M, const uint8_
   return out;
 }
 
-template <int R>
 __global__ void __launch_bounds__(1024, 1) encode_unigram_lane_kernel(const KModel M, const KBatch B, uint8_t *slabs,
-                                                                       uint32_t cap) {
+                                                                       uint32_t cap, uint32_t R) {
   extern __shared__ __align__(128) uint8_t smem[];
-  uint64_t *mbar = reinterpret_cast<uint64_t *>(smem);
-  uint32_t *s_link = reinterpret_cast<uint32_t *>(smem + 16);
-  uint32_t *s_val = s_link + M.hot_link;
-  uint32_t *s_tab = s_val + M.hot_val;
-  uint8_t *rings = reinterpret_cast<uint8_t *>(s_tab) + kLaneTableBytes;
-  // normalizer fast-path tables -> shared memory (L1 is tiny under this carve-out)
+  uint32_t *s_tab = reinterpret_cast<uint32_t *>(smem);
+  uint8_t *rings = smem + kLaneTableBytes;
+  // normalizer fast-path tables -> shared memory
   for (uint32_t i = threadIdx.x; i < kLaneTableBytes / 4; i += blockDim.x) {
     uint32_t v;
     if (i < 8) v = M.cm_lead[i];
@@ -271,13 +267,10 @@ __global__ void __launch_bounds__(1024, 1) encode_unigram_lane_kernel(const KMod
     else v = static_cast<uint32_t>(M.cm_solo[i - 8 - 1024]);
     s_tab[i] = v;
   }
-  stage_hot_trie(M, mbar, s_link, s_val);
   __syncthreads();
-  const HotTrie H{s_link, s_val, M.trie_link, M.trie_val, M.hot_link, M.hot_val};
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t warp_in_cta = threadIdx.x >> 5;
   const uint32_t warp_global = blockIdx.x * (blockDim.x >> 5) + warp_in_cta;
-  constexpr uint32_t RM = R - 1;
   LaneCtx c;
   {
     uint8_t *ring = rings + static_cast<size_t>(warp_in_cta) * (R * 32 * 8);
@@ -290,7 +283,8 @@ __global__ void __launch_bounds__(1024, 1) encode_unigram_lane_kernel(const KMod
     c.s_pair = s_tab + 8;
     c.s_solo = reinterpret_cast<const int32_t *>(s_tab + 8 + 1024);
   }
-  const uint32_t root = H.link(0);
+  const uint2 *node2 = M.trie_node2;
+  const uint32_t root = __ldg(&node2[0]).x;
   const bool bf = M.flags & kFlagByteFallback;
   const bool regular = M.flags & kFlagRegularScores;
 
@@ -320,110 +314,126 @@ __global__ void __launch_bounds__(1024, 1) encode_unigram_lane_kernel(const KMod
     }
     __syncwarp();
     // ---------------- K2: flat state machine, one trie transition per trip ----------------
-    uint32_t s = 0, k = 0, l = root, mblen = 1, nlog = 0;
+    // text window: words w0..w3 = bytes [4*aw, 4*aw+16), aw = s >> 2; `cur` streams the bytes
+    // from the walk position k (low byte first).
+    uint32_t s = 0, ss = 0 /* ring slot of s */, k = 0, l = root, mblen = 1, nlog = 0;
     bool has_single = false, done = n == 0;
     float base = 0.f;
     bool base_regular = regular;  // base == 0
-    uint32_t aw = 0;              // anchor word of the text window
-    uint32_t t0 = 0, t1 = 0, t2 = 0, t3 = 0;  // text bytes [4*aw, 4*aw+16)
-    auto text_at = [&](uint32_t kk) -> uint32_t {
-      const uint32_t d = kk - 4u * aw;
-      uint32_t w;
-      if (d < 16u) {
-        const uint32_t ws = d >> 2;
-        w = ws == 0 ? t0 : (ws == 1 ? t1 : (ws == 2 ? t2 : t3));
-      } else {
-        w = c.text_w[static_cast<size_t>(kk >> 2) * 32];  // beyond the window: long piece, rare
-      }
-      return (w >> ((kk & 3u) * 8u)) & 0xFFu;
+    uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+    unsigned long long cur = 0;
+    auto window_low = [&]() -> unsigned long long {  // bytes s .. s+7
+      const uint32_t sh = (s & 3u) * 8u;
+      return static_cast<unsigned long long>(__funnelshift_r(w0, w1, sh)) |
+             (static_cast<unsigned long long>(__funnelshift_r(w1, w2, sh)) << 32);
+    };
+    auto window_high = [&]() -> unsigned long long {  // bytes s+8 .. (at least s+12)
+      const uint32_t sh = (s & 3u) * 8u;
+      return static_cast<unsigned long long>(__funnelshift_r(w2, w3, sh)) |
+             (static_cast<unsigned long long>(w3 >> sh) << 32);
     };
     if (!done) {
-      for (uint32_t r = 0; r < static_cast<uint32_t>(R); ++r) c.rb[r * 32] = 0u;  // all positions unset
+      for (uint32_t r = 0; r < R; ++r) c.rb[r * 32] = 0u;  // all positions unset
       c.rs[0] = 0.f;
-      t0 = c.text_w[0]; t1 = c.text_w[32]; t2 = c.text_w[64]; t3 = c.text_w[96];
-      mblen = one_char_len(t0 & 0xFFu);
+      w0 = c.text_w[0]; w1 = c.text_w[32]; w2 = c.text_w[64]; w3 = c.text_w[96];
+      mblen = one_char_len(w0 & 0xFFu);
       if (mblen > n) mblen = n;
+      cur = window_low();
     }
     while (__any_sync(0xFFFFFFFFu, !done)) {
       if (!done) {
-        bool ok = false;
-        uint32_t v = 0, nl = 0;
+        bool end_walk = true;
         if (k < n) {
-          const uint32_t ch = text_at(k);
-          v = (l >> kLinkBaseShift) ^ ch;
-          nl = H.link(v);
-          ok = (nl & kLinkLabelMask) == ch;
-        }
-        if (ok) {
-          ++k;
-          l = nl;
-          const uint32_t kind = (nl >> kLinkKindShift) & 3u;
-          if (kind == kKindNormal || kind == kKindUserDefined) {
-            const uint32_t plen = k - s;
-            const uint32_t slot = (k & RM) * 32;
-            const float cur = c.rs[slot];
-            const bool unset = c.rb[slot] == 0u;
-            float ns;
-            bool better;
-            if (kind == kKindNormal && base_regular) {
-              // Exact float formulation of the reference's double comparison (Q1).  With
-              // |score|, |base| in {0} U [2^-10, 2^18) the double sum a + b is exact, so
-              // (float)cand == fl(a + b) and cand > cur  <=>  ns > cur || (ns == cur && err > 0),
-              // err being the exact rounding error of the float add (Knuth two-sum).
-              const float a = __uint_as_float(H.val(v));
-              ns = __fadd_rn(a, base);
-              const float bb = __fsub_rn(ns, a);
-              const float err = __fadd_rn(__fsub_rn(a, __fsub_rn(ns, bb)), __fsub_rn(base, bb));
-              better = unset || ns > cur || (ns == cur && err > 0.f);
-            } else {
-              const double sc = kind == kKindNormal
-                                    ? static_cast<double>(__uint_as_float(H.val(v)))
-                                    : static_cast<double>(__fmul_rn(static_cast<float>(plen), M.max_score)) - 0.1;
-              const double cand = sc + static_cast<double>(base);
-              better = unset || cand > static_cast<double>(cur);
-              ns = static_cast<float>(cand);
-            }
-            if (better) {
-              c.rs[slot] = ns;
-              c.rb[slot] = (plen << 24) | v;
-            }
-            has_single |= plen == mblen;
+          const uint32_t d = k - s;
+          uint32_t ch;
+          if (d >= 13u) {  // beyond the register window: long piece, rare
+            ch = (c.text_w[static_cast<size_t>(k >> 2) * 32] >> ((k & 3u) * 8u)) & 0xFFu;
+          } else {
+            if (d == 8u) cur = window_high();
+            ch = static_cast<uint32_t>(cur) & 0xFFu;
+            cur >>= 8;
           }
-        } else {
+          const uint32_t v = (l >> kLinkBaseShift) ^ ch;
+          const uint2 nd = __ldg(&node2[v]);  // {link, child mask}: one 8-byte load (L1/L2)
+          if ((nd.x & kLinkLabelMask) == ch) {
+            ++k;
+            l = nd.x;
+            const uint32_t kind = (nd.x >> kLinkKindShift) & 3u;
+            if (kind == kKindNormal || kind == kKindUserDefined) {
+              const uint32_t plen = k - s;
+              uint32_t sl = ss + plen;
+              if (sl >= R) sl -= R;
+              sl *= 32;
+              const float curs = c.rs[sl];
+              const bool unset = c.rb[sl] == 0u;
+              float ns;
+              bool better;
+              if (kind == kKindNormal && base_regular) {
+                // Exact float formulation of the reference's double comparison (Q1).  With
+                // |score|, |base| in {0} U [2^-10, 2^18) the double sum a + b is exact, so
+                // (float)cand == fl(a + b) and cand > cur <=> ns > cur || (ns == cur && err > 0),
+                // err being the exact rounding error of the float add (Knuth two-sum).
+                const float a = __uint_as_float(__ldg(M.trie_val + v));
+                ns = __fadd_rn(a, base);
+                const float bb = __fsub_rn(ns, a);
+                const float err = __fadd_rn(__fsub_rn(a, __fsub_rn(ns, bb)), __fsub_rn(base, bb));
+                better = unset || ns > curs || (ns == curs && err > 0.f);
+              } else {
+                const double sc = kind == kKindNormal
+                                      ? static_cast<double>(__uint_as_float(__ldg(M.trie_val + v)))
+                                      : static_cast<double>(__fmul_rn(static_cast<float>(plen), M.max_score)) - 0.1;
+                const double cand = sc + static_cast<double>(base);
+                better = unset || cand > static_cast<double>(curs);
+                ns = static_cast<float>(cand);
+              }
+              if (better) {
+                c.rs[sl] = ns;
+                c.rb[sl] = (plen << 24) | v;
+              }
+              has_single |= plen == mblen;
+            }
+            // early termination: if the node has no child on the next byte the failing
+            // probe (and its cold miss) is skipped and the start transition happens now
+            if (k < n) {
+              uint32_t nb;
+              const uint32_t d2 = k - s;
+              if (d2 >= 13u) nb = (c.text_w[static_cast<size_t>(k >> 2) * 32] >> ((k & 3u) * 8u)) & 0xFFu;
+              else nb = d2 == 8u ? static_cast<uint32_t>(window_high()) & 0xFFu : static_cast<uint32_t>(cur) & 0xFFu;
+              end_walk = !((nd.y >> (nb & 31u)) & 1u);
+            }
+          }
+        }
+        if (end_walk) {
           // the walk from s is over (traverse() == -2, or end of text)
+          uint32_t sl = ss + mblen;
+          if (sl >= R) sl -= R;
           if (!has_single) {  // UNK edge, unigram_model.cc:995-1005
-            const uint32_t slot = ((s + mblen) & RM) * 32;
             const float cand = __fadd_rn(M.unk_score, base);
-            if (c.rb[slot] == 0u || cand > c.rs[slot]) {
-              c.rs[slot] = cand;
-              c.rb[slot] = (mblen << 24) | kLaneUnk;
+            if (c.rb[sl * 32] == 0u || cand > c.rs[sl * 32]) {
+              c.rs[sl * 32] = cand;
+              c.rb[sl * 32] = (mblen << 24) | kLaneUnk;
             }
           }
           // position s leaves the window; only character starts are ever targets, so its
           // slot is the only one that has to be cleared for position s + R
-          c.rb[(s & RM) * 32] = 0u;
+          c.rb[ss * 32] = 0u;
           s += mblen;
-          const uint32_t slot = (s & RM) * 32;
+          ss = sl;
           // position s is final: append (plen | previous char length | unit) to the log
-          c.log[static_cast<size_t>(nlog) * 32] = c.rb[slot] | ((mblen - 1u) << 22);
+          c.log[static_cast<size_t>(nlog) * 32] = c.rb[ss * 32] | ((mblen - 1u) << 22);
           ++nlog;
           if (s >= n) {
             done = true;
           } else {
-            base = c.rs[slot];
+            base = c.rs[ss * 32];
             base_regular = regular && (base == 0.f || (fabsf(base) >= 0.0009765625f && fabsf(base) < 262144.f));
             // slide the text window so that it is anchored at s; prefetch the new tail word
-            const uint32_t naw = s >> 2;
-            if (naw != aw) {
-              if (naw == aw + 1) { t0 = t1; t1 = t2; t2 = t3; t3 = c.text_w[static_cast<size_t>(naw + 3) * 32]; }
-              else {
-                t0 = c.text_w[static_cast<size_t>(naw) * 32]; t1 = c.text_w[static_cast<size_t>(naw + 1) * 32];
-                t2 = c.text_w[static_cast<size_t>(naw + 2) * 32]; t3 = c.text_w[static_cast<size_t>(naw + 3) * 32];
-              }
-              aw = naw;
+            if ((s >> 2) != ((s - mblen) >> 2)) {
+              w0 = w1; w1 = w2; w2 = w3;
+              w3 = c.text_w[static_cast<size_t>((s >> 2) + 3) * 32];
             }
-            const uint32_t lead = (t0 >> ((s & 3u) * 8u)) & 0xFFu;
-            mblen = one_char_len(lead);
+            cur = window_low();
+            mblen = one_char_len(static_cast<uint32_t>(cur) & 0xFFu);
             if (mblen > n - s) mblen = n - s;
             k = s;
             l = root;

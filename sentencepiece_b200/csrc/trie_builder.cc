@@ -146,6 +146,12 @@ bool BuildDeviceTrie(const std::vector<TrieKey> &keys, int vocab_size, DeviceTri
     }
   }
   // ---- 3. emit -----------------------------------------------------------
+  out->cmask.assign(link.size(), 0u);
+  for (uint32_t n = 0; n < nodes.size(); ++n) {
+    uint32_t m = 0;
+    for (const auto &c : kids[n]) m |= 1u << (c.first & 31u);
+    out->cmask[nodes[n].unit] = m;
+  }
   out->val.assign(link.size(), 0xFFFFFFFFu);
   out->id.assign(link.size(), -1);
   out->unit_of_id.assign(static_cast<size_t>(vocab_size), 0xFFFFFFFFu);

@@ -50,6 +50,7 @@ struct DeviceTrie {
   std::vector<uint32_t> link;
   std::vector<uint32_t> val;
   std::vector<int32_t> id;
+  std::vector<uint32_t> cmask;  // per unit: OR over children c of 1 << (c & 31); 0 = leaf (early walk termination)
   std::vector<uint32_t> unit_of_id;  // vocab id -> unit (0xFFFFFFFF if the id is not a key)
   uint32_t max_key_len = 0;
   uint32_t max_matches_per_start = 0;  // == trie_results_size_ of unigram_model.cc:635-644

@@ -30,7 +30,7 @@ d_ido = torch.empty(n + 1, dtype=torch.int64, device=dev)
 if configs:
     grid = [tuple(int(x) for x in c.split(",")) for c in configs]
 else:
-    grid = [(1, 512, 0), (1, 768, 0), (1, 832, 0)]
+    grid = [(1, 512, 0), (1, 768, 0), (1, 1024, 0)]
 ref = None
 for G, thr, capn in grid:
     try:
