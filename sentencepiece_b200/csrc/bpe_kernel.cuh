@@ -348,7 +348,8 @@ __global__ void __launch_bounds__(512, 1) encode_bpe_kernel(const KModel M, cons
     uint32_t sent = 0;
     if (T.lane == 0) sent = atomicAdd(B.work_counter, 1u);
     sent = __shfl_sync(0xFFFFFFFFu, sent, 0);
-    if (sent >= B.n) break;
+    if (sent >= (B.sub_list ? B.sub_n : B.n)) break;
+    if (B.sub_list) sent = B.sub_list[2 * sent];
     const unsigned long long off = B.offsets[sent];
     const unsigned long long len64 = B.offsets[sent + 1] - off;
     bool fits = len64 + 32ull <= bm.stage_cap;

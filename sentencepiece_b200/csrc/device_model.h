@@ -82,6 +82,9 @@ struct KBatch {
   uint32_t *deferred;            // list of sentence indices that did not fit shared memory
   uint32_t *status;              // [0] deferred count, [1] error flag, [2] overflow flag
   // long-sentence path: sentence list + per-entry scratch slab
+  // second-chance pass over the sentences a lane kernel deferred: (sentence, need) pairs
+  const uint32_t *sub_list;
+  uint32_t sub_n;
   const uint32_t *long_list;
   uint32_t long_n;
   uint8_t *long_scratch;

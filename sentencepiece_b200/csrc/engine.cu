@@ -23,6 +23,7 @@
 
 #include "../../include/spm_b200.h"
 #include "bpe_kernel.cuh"
+#include "bpe_lane_kernel.cuh"
 #include "device_model.h"
 #include "kernels.cuh"
 #include "lane_kernel.cuh"
@@ -145,7 +146,7 @@ struct spm_engine {
   DevBuf<uint8_t> d_bytes, d_tmp_norm, d_norm, d_long_scratch, d_lane_slabs;
   DevBuf<uint64_t> d_offsets;
   DevBuf<int32_t> d_tmp_ids, d_ids;
-  DevBuf<uint32_t> d_tmp_tok_end, d_tok_end, d_tmp_n2o, d_n2o, d_sent_count, d_norm_len, d_deferred, d_long_list, d_ctrl32;
+  DevBuf<uint32_t> d_tmp_tok_end, d_tok_end, d_tmp_n2o, d_n2o, d_sent_count, d_norm_len, d_deferred, d_deferred2, d_long_list, d_ctrl32;
   DevBuf<unsigned long long> d_sent_start, d_norm_start, d_id_offsets, d_norm_offsets, d_n2o_offsets, d_block_sums,
       d_ctrl64, d_long_off;
   PinBuf<int32_t> h_ids;
@@ -456,6 +457,7 @@ int spm_engine::configure_kernel_attrs() {
   CUDA_TRY(set_smem(encode_unigram_long_kernel<false>, mx));
   CUDA_TRY(set_smem(encode_unigram_long_kernel<true>, mx));
   CUDA_TRY(set_smem(encode_unigram_lane_kernel, mx));
+  CUDA_TRY(set_smem(encode_bpe_lane_kernel, mx));
   CUDA_TRY(set_smem(encode_unigram_warp_kernel<512>, mx));
   CUDA_TRY(set_smem(encode_unigram_warp_kernel<1024>, mx));
   CUDA_TRY(set_smem(encode_bpe_kernel<false>, mx));
@@ -481,6 +483,8 @@ int spm_engine::run_device(const uint8_t *d_bytes_base, const uint64_t *d_offs, 
   LaunchGeom geom = plan_geometry(*this, spans, useG, tile_threads, ncap, K);
   // fast unigram path: warp per sentence, register-resident Viterbi window
   const bool lane_path = !bpe && !spans && trie.max_key_len <= 62 && G == 1;
+  const bool bpe_lane_path = bpe && !spans && G == 1 && (km.flags & kFlagBpeWordSplit) && (km.flags & kFlagEscapeWs) &&
+                             !(km.flags & (kFlagHasUserSymbols | kFlagHasUnused));
   const bool warp_path = !bpe && !spans && trie.max_key_len <= 32 && G == 32;
   const int launch_threads = warp_path ? threads : tile_threads;
   const uint32_t laneR = trie.max_key_len + 2;  // ring slots: positions [s, s + max piece length]
@@ -494,6 +498,14 @@ int spm_engine::run_device(const uint8_t *d_bytes_base, const uint64_t *d_offs, 
     geom.hot_val = static_cast<uint32_t>(std::min<size_t>(km.trie_units, (hot - static_cast<size_t>(geom.hot_link) * 4) / 4)) & ~3u;
     geom.smem_bytes = static_cast<uint32_t>(16 + static_cast<size_t>(geom.hot_link + geom.hot_val) * 4 +
                                             static_cast<size_t>(geom.tiles) * geom.tile_bytes);
+  }
+  if (bpe_lane_path) {
+    geom.tiles = tile_threads / 32;
+    geom.tile_bytes = kBpeLaneWarpBytes;
+    geom.hot_link = geom.hot_val = 0;
+    geom.smem_bytes = static_cast<uint32_t>(kLaneTableBytes + static_cast<size_t>(geom.tiles) * geom.tile_bytes);
+    const size_t warps_total = static_cast<size_t>(sm_count) * ctas_per_sm * geom.tiles;
+    CUDA_TRY(d_lane_slabs.ensure(warps_total * lane_slab_bytes(lane_cap) + 256));
   }
   if (lane_path) {
     geom.tiles = threads / 32;
@@ -515,9 +527,10 @@ int spm_engine::run_device(const uint8_t *d_bytes_base, const uint64_t *d_offs, 
   CUDA_TRY(d_sent_start.ensure(n));
   CUDA_TRY(d_sent_count.ensure(n));
   CUDA_TRY(d_deferred.ensure(2 * n + 2));
-  CUDA_TRY(d_ctrl32.ensure(8));
+  CUDA_TRY(d_ctrl32.ensure(16));
+  CUDA_TRY(d_deferred2.ensure(2 * n + 2));
   CUDA_TRY(d_ctrl64.ensure(4));
-  CUDA_TRY(h_ctrl32.ensure(8));
+  CUDA_TRY(h_ctrl32.ensure(16));
   CUDA_TRY(h_ctrl64.ensure(4));
   if (spans) {
     CUDA_TRY(d_norm_start.ensure(n));
@@ -532,7 +545,7 @@ int spm_engine::run_device(const uint8_t *d_bytes_base, const uint64_t *d_offs, 
       CUDA_TRY(d_tmp_norm.ensure(norm_cap));
       CUDA_TRY(d_tmp_n2o.ensure(norm_cap));
     }
-    CUDA_TRY(cudaMemsetAsync(d_ctrl32.p, 0, 8 * sizeof(uint32_t), st));
+    CUDA_TRY(cudaMemsetAsync(d_ctrl32.p, 0, 16 * sizeof(uint32_t), st));
     CUDA_TRY(cudaMemsetAsync(d_ctrl64.p, 0, 4 * sizeof(unsigned long long), st));
     KBatch B{};
     B.bytes = d_bytes_base;
@@ -556,7 +569,9 @@ int spm_engine::run_device(const uint8_t *d_bytes_base, const uint64_t *d_offs, 
     B.tile_bytes = geom.tile_bytes;
 
     CUDA_TRY(cudaEventRecord(ev[0], st));
-    if (bpe) {
+    if (bpe_lane_path) {
+      encode_bpe_lane_kernel<<<grid, tile_threads, geom.smem_bytes, st>>>(M, B, d_lane_slabs.p, lane_cap);
+    } else if (bpe) {
       if (spans) encode_bpe_kernel<true><<<grid, tile_threads, geom.smem_bytes, st>>>(M, B);
       else encode_bpe_kernel<false><<<grid, tile_threads, geom.smem_bytes, st>>>(M, B);
     } else if (lane_path) {
@@ -578,15 +593,53 @@ int spm_engine::run_device(const uint8_t *d_bytes_base, const uint64_t *d_offs, 
     CUDA_TRY(cudaGetLastError());
     ++last_launches;
     CUDA_TRY(cudaEventRecord(ev[1], st));
-    CUDA_TRY(cudaMemcpyAsync(h_ctrl32.p, d_ctrl32.p, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(h_ctrl32.p, d_ctrl32.p, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(h_ctrl64.p, d_ctrl64.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     uint32_t n_def = h_ctrl32.p[0];
+    const uint32_t *def_list = d_deferred.p;
+    if (n_def && (lane_path || bpe_lane_path)) {
+      // ---- second chance: the sentences a lane kernel could not take (long words, long
+      //      sentences) go through the shared-memory warp kernels before the HBM-scratch path ----
+      last_deferred = n_def;
+      LaunchGeom g2{};
+      g2.tiles = tile_threads / 32;
+      g2.tile_bytes = bpe ? bpe_tile_bytes(ncap, false) : tile_bytes_for(ncap, 32, K, false);
+      const size_t fixed2 = 16 + static_cast<size_t>(g2.tiles) * g2.tile_bytes + 128;
+      const size_t hot2 = smem_optin > fixed2 ? smem_optin - fixed2 : 0;
+      KModel M2 = km;
+      M2.hot_link = static_cast<uint32_t>(std::min<size_t>(km.trie_units, (hot2 * 3 / 4) / 4)) & ~3u;
+      M2.hot_val = static_cast<uint32_t>(std::min<size_t>(km.trie_units, (hot2 - static_cast<size_t>(M2.hot_link) * 4) / 4)) & ~3u;
+      const uint32_t smem2 = static_cast<uint32_t>(16 + static_cast<size_t>(M2.hot_link + M2.hot_val) * 4 +
+                                                   static_cast<size_t>(g2.tiles) * g2.tile_bytes);
+      KBatch B2 = B;
+      B2.sub_list = d_deferred.p;
+      B2.sub_n = n_def;
+      B2.deferred = d_deferred2.p;
+      B2.status = d_ctrl32.p + 8;
+      B2.work_counter = d_ctrl32.p + 12;
+      B2.ncap = ncap;
+      B2.tile_bytes = g2.tile_bytes;
+      const int grid2 = static_cast<int>(std::min<uint32_t>(static_cast<uint32_t>(grid), (n_def + g2.tiles - 1) / g2.tiles));
+      if (bpe) encode_bpe_kernel<false><<<grid2, tile_threads, smem2, st>>>(M2, B2);
+      else encode_unigram_kernel<32, false><<<grid2, tile_threads, smem2, st>>>(M2, B2);
+      CUDA_TRY(cudaGetLastError());
+      ++last_launches;
+      CUDA_TRY(cudaMemcpyAsync(h_ctrl32.p, d_ctrl32.p, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaMemcpyAsync(h_ctrl64.p, d_ctrl64.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaStreamSynchronize(st));
+      n_def = h_ctrl32.p[8];
+      h_ctrl32.p[1] |= h_ctrl32.p[9];
+      h_ctrl32.p[2] |= h_ctrl32.p[10];
+      def_list = d_deferred2.p;
+      M.hot_link = M2.hot_link;  // the long kernels stage the same hot prefix
+      M.hot_val = M2.hot_val;
+    }
     if (n_def) {
       // ---- long sentences: warp per sentence, scratch slab in HBM ----
-      last_deferred = n_def;
+      last_deferred = std::max<uint64_t>(last_deferred, n_def);
       CUDA_TRY(h_deferred.ensure(2 * static_cast<size_t>(n_def)));
-      CUDA_TRY(cudaMemcpyAsync(h_deferred.p, d_deferred.p, 2ull * n_def * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaMemcpyAsync(h_deferred.p, def_list, 2ull * n_def * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
       // lengths of the deferred sentences whose normalized size is unknown
       std::vector<uint64_t> two(2);
       std::vector<unsigned long long> offs(n_def + 1, 0);
@@ -627,9 +680,11 @@ int spm_engine::run_device(const uint8_t *d_bytes_base, const uint64_t *d_offs, 
       }
       CUDA_TRY(cudaGetLastError());
       ++last_launches;
-      CUDA_TRY(cudaMemcpyAsync(h_ctrl32.p, d_ctrl32.p, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaMemcpyAsync(h_ctrl32.p, d_ctrl32.p, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
       CUDA_TRY(cudaMemcpyAsync(h_ctrl64.p, d_ctrl64.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
       CUDA_TRY(cudaStreamSynchronize(st));
+      h_ctrl32.p[1] |= h_ctrl32.p[9];
+      h_ctrl32.p[2] |= h_ctrl32.p[10];
     }
     if (h_ctrl32.p[1]) {
       set_error("encode failed: internal consistency check (status " + std::to_string(h_ctrl32.p[1]) + ")");
@@ -782,7 +837,7 @@ void spm_engine_destroy(spm_engine *e) {
   e->d_types.release(); e->d_scores.release(); e->d_bytes.release(); e->d_tmp_norm.release(); e->d_norm.release();
   e->d_long_scratch.release(); e->d_offsets.release(); e->d_tmp_ids.release(); e->d_ids.release();
   e->d_tmp_tok_end.release(); e->d_tok_end.release(); e->d_tmp_n2o.release(); e->d_n2o.release();
-  e->d_sent_count.release(); e->d_norm_len.release(); e->d_deferred.release(); e->d_long_list.release();
+  e->d_sent_count.release(); e->d_norm_len.release(); e->d_deferred.release(); e->d_deferred2.release(); e->d_long_list.release();
   e->d_ctrl32.release(); e->d_sent_start.release(); e->d_norm_start.release(); e->d_id_offsets.release();
   e->d_norm_offsets.release(); e->d_n2o_offsets.release(); e->d_block_sums.release(); e->d_ctrl64.release();
   e->d_long_off.release();

@@ -711,9 +711,11 @@ __global__ void __launch_bounds__(512, 1) encode_unigram_kernel(const KModel M, 
     uint32_t first = 0;
     if ((threadIdx.x & 31) == 0) first = atomicAdd(B.work_counter, static_cast<uint32_t>(TPW));
     first = __shfl_sync(0xFFFFFFFFu, first, 0);
-    if (first >= B.n) break;
-    const uint32_t sent = first + tile_in_warp;
-    if (sent < B.n) {
+    const uint32_t work_n = B.sub_list ? B.sub_n : B.n;
+    if (first >= work_n) break;
+    const uint32_t widx = first + tile_in_warp;
+    if (widx < work_n) {
+      const uint32_t sent = B.sub_list ? B.sub_list[2 * widx] : widx;
       const unsigned long long off = B.offsets[sent];
       const unsigned long long len64 = B.offsets[sent + 1] - off;
       bool fits = len64 + 32ull <= tm.stage_cap;

@@ -278,9 +278,11 @@ __global__ void __launch_bounds__(MAXT, 1) encode_unigram_warp_kernel(const KMod
     uint32_t first = 0;
     if (lane == 0) first = atomicAdd(B.work_counter, kClaim);
     first = __shfl_sync(0xFFFFFFFFu, first, 0);
-    if (first >= B.n) break;
-    const uint32_t last = first + kClaim < B.n ? first + kClaim : B.n;
-    for (uint32_t sent = first; sent < last; ++sent) {
+    const uint32_t work_n = B.sub_list ? B.sub_n : B.n;
+    if (first >= work_n) break;
+    const uint32_t last = first + kClaim < work_n ? first + kClaim : work_n;
+    for (uint32_t wi = first; wi < last; ++wi) {
+      const uint32_t sent = B.sub_list ? B.sub_list[2 * wi] : wi;
       const unsigned long long off = B.offsets[sent];
       const unsigned long long len64 = B.offsets[sent + 1] - off;
       bool fits = len64 + 32ull <= wm.stage_cap;
