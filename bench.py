@@ -324,7 +324,7 @@ def main():
         kernel_ms = statistics.mean(main_ms)
         achieved = alg_bytes / (kernel_ms / 1e3) / 1e9
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "kernel": "encode_%s_kernel" % ("bpe" if "bpe" in model else "unigram"),
+                    "traffic": None, "kernel": "encode_%s_lane_kernel" % ("bpe" if "bpe" in model else "unigram"),
                     "kernel_ms": kernel_ms, "all_kernels_ms": statistics.mean(all_ms),
                     "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                     "note": "latency/L2-bound integer path: ~570 dependent trie lookups per sentence vs ~250 B of "

@@ -28,7 +28,7 @@ constexpr uint32_t kBpeWordSyms = 24;                      // symbols of one wor
 constexpr uint32_t kBpeLaneWarpBytes = kBpeWordSyms * 32 * 4 * 3;  // sym, pn, ps
 constexpr uint32_t kBpeDead = 0x3FFFFFu;                   // 22-bit node field: not a trie path / not a piece
 
-__global__ void __launch_bounds__(512, 1) encode_bpe_lane_kernel(const KModel M, const KBatch B, uint8_t *slabs,
+__global__ void __launch_bounds__(768, 1) encode_bpe_lane_kernel(const KModel M, const KBatch B, uint8_t *slabs,
                                                                   uint32_t cap) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint32_t *s_tab = reinterpret_cast<uint32_t *>(smem);

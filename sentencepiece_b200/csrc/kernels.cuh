@@ -831,7 +831,8 @@ __global__ void __launch_bounds__(256) scan_write_gather_kernel(const uint32_t *
                                                                 const unsigned long long *src_start,
                                                                 const ElemT *src, ElemT *dst,
                                                                 const uint32_t *src2, uint32_t *dst2,
-                                                                unsigned long long dst_cap, uint32_t extra) {
+                                                                unsigned long long dst_cap, uint32_t extra,
+                                                                unsigned long long off_base) {
   __shared__ unsigned long long sh_off[kScanChunk + 1];
   __shared__ unsigned long long warp_sums[8];
   const uint32_t base = blockIdx.x * kScanChunk;
@@ -858,9 +859,9 @@ __global__ void __launch_bounds__(256) scan_write_gather_kernel(const uint32_t *
   for (int k = 0; k < 8; ++k) {
     const uint32_t i = base + threadIdx.x * 8 + k;
     sh_off[threadIdx.x * 8 + k] = run;
-    if (i < n) offsets[i] = run;
+    if (i < n) offsets[i] = run + off_base;  // off_base: ids of the batch's earlier chunks (pipelined host API)
     run += c[k];
-    if (i + 1 == n) offsets[n] = run;
+    if (i + 1 == n) offsets[n] = run + off_base;
   }
   __syncthreads();
   if (dst == nullptr) return;
