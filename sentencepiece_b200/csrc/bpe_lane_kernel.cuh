@@ -37,7 +37,12 @@ __global__ void __launch_bounds__(768, 1) encode_bpe_lane_kernel(const KModel M,
     uint32_t v;
     if (i < 8) v = M.cm_lead[i];
     else if (i < 8 + 1024) v = M.cm_pair[i - 8];
-    else v = static_cast<uint32_t>(M.cm_solo[i - 8 - 1024]);
+    else if (i < 8 + 1024 + 128) v = static_cast<uint32_t>(M.cm_solo[i - 8 - 1024]);
+    else {  // plain ASCII bytes: no charsmap rule starts with them and they are not the space
+      const uint32_t wq = i - (8 + 1024 + 128);
+      v = ~((M.flags & kFlagHasCharsmap) ? M.cm_lead[wq] : 0u);
+      if (wq == 1) v &= ~1u;  // ' ' = 0x20
+    }
     s_tab[i] = v;
   }
   __syncthreads();
@@ -60,6 +65,7 @@ __global__ void __launch_bounds__(768, 1) encode_bpe_lane_kernel(const KModel M,
     c.s_lead = s_tab;
     c.s_pair = s_tab + 8;
     c.s_solo = reinterpret_cast<const int32_t *>(s_tab + 8 + 1024);
+    c.s_plain = s_tab + 8 + 1024 + 128;
   }
   const uint2 *node2 = M.trie_node2;
   const uint32_t root = __ldg(&node2[0]).x;

@@ -38,7 +38,7 @@ __host__ __device__ inline unsigned long long lane_slab_bytes(uint32_t cap) {
   return (static_cast<unsigned long long>(cap / 4 + 4) + (cap + 4)) * 32ull * 4ull;
 }
 // shared memory for the normalizer's fast-path tables
-constexpr uint32_t kLaneTableBytes = 32 + 4096 + 512;  // cm_lead[8] + cm_pair[1024] + cm_solo[128]
+constexpr uint32_t kLaneTableBytes = 32 + 4096 + 512 + 16;  // cm_lead[8] + cm_pair[1024] + cm_solo[128] + plain[4]
 
 struct LaneCtx {
   uint32_t *text_w;  // + word*32 (already offset by lane)
@@ -47,6 +47,7 @@ struct LaneCtx {
   uint32_t *rb;      // ring back-pointers (plen<<24 | unit), 0 = unset
   const uint32_t *s_lead, *s_pair;
   const int32_t *s_solo;
+  const uint32_t *s_plain;  // bit b: ASCII byte b is copied verbatim (no rule starts with it, not a space)
 };
 
 // Sequential byte stream over a lane's input: 16-byte aligned chunks (next chunk prefetched)
@@ -128,6 +129,22 @@ __device__ __forceinline__ uint32_t lane_normalize(const KModel &M, const uint8_
   // One chunk of NormalizePrefix (normalizer.cc:195-253) + the emit logic of Normalize (:131-163)
   while (pos < len) {
     const uint32_t rem = len - pos;
+    // ---- fast path: four plain ASCII bytes at once (each is its own identity chunk) ----
+    if (started && !has_user && rem >= 4) {
+      const uint32_t w4 = static_cast<uint32_t>(S.win);
+      const uint32_t c0 = w4 & 0xFFu, c1 = (w4 >> 8) & 0xFFu, c2 = (w4 >> 16) & 0xFFu, c3 = w4 >> 24;
+      if (!(w4 & 0x80808080u) && ((c.s_plain[c0 >> 5] >> (c0 & 31u)) & (c.s_plain[c1 >> 5] >> (c1 & 31u)) &
+                                  (c.s_plain[c2 >> 5] >> (c2 & 31u)) & (c.s_plain[c3 >> 5] >> (c3 & 31u)) & 1u)) {
+        const uint32_t r = (out & 3u) * 8u;
+        if (out + 3 < cap) c.text_w[static_cast<size_t>(out >> 2) * 32] = acc | (w4 << r); else overflow = true;
+        acc = r ? (w4 >> (32u - r)) : 0u;
+        out += 4;
+        is_prev_space = false;
+        pos += 4;
+        S.consume(4);
+        continue;
+      }
+    }
     const uint32_t b = S.peek(0);
     uint32_t consumed = 1;
     // replacement string: kind + (pointer | inline bytes)
@@ -264,7 +281,12 @@ __global__ void __launch_bounds__(1024, 1) encode_unigram_lane_kernel(const KMod
     uint32_t v;
     if (i < 8) v = M.cm_lead[i];
     else if (i < 8 + 1024) v = M.cm_pair[i - 8];
-    else v = static_cast<uint32_t>(M.cm_solo[i - 8 - 1024]);
+    else if (i < 8 + 1024 + 128) v = static_cast<uint32_t>(M.cm_solo[i - 8 - 1024]);
+    else {  // plain ASCII bytes: no charsmap rule starts with them and they are not the space
+      const uint32_t wq = i - (8 + 1024 + 128);
+      v = ~((M.flags & kFlagHasCharsmap) ? M.cm_lead[wq] : 0u);
+      if (wq == 1) v &= ~1u;  // ' ' = 0x20
+    }
     s_tab[i] = v;
   }
   __syncthreads();
@@ -282,6 +304,7 @@ __global__ void __launch_bounds__(1024, 1) encode_unigram_lane_kernel(const KMod
     c.s_lead = s_tab;
     c.s_pair = s_tab + 8;
     c.s_solo = reinterpret_cast<const int32_t *>(s_tab + 8 + 1024);
+    c.s_plain = s_tab + 8 + 1024 + 128;
   }
   const uint2 *node2 = M.trie_node2;
   const uint32_t root = __ldg(&node2[0]).x;
