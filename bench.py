@@ -323,12 +323,19 @@ def main():
         alg_bytes = total_bytes + 8 * n + 4 * total_ids  # input + 4 + 4*ids + 4 per sentence
         kernel_ms = statistics.mean(main_ms)
         achieved = alg_bytes / (kernel_ms / 1e3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tpath):
+            t = json.load(open(tpath)).get(args.workload)
+            if t and t["sentences"] == n:  # per launch, same batch size as the ncu capture
+                traffic = t["traffic_bytes"]
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "kernel": "encode_%s_lane_kernel" % ("bpe" if "bpe" in model else "unigram"),
+                    "traffic": traffic, "kernel": "encode_%s_lane_kernel" % ("bpe" if "bpe" in model else "unigram"),
                     "kernel_ms": kernel_ms, "all_kernels_ms": statistics.mean(all_ms),
                     "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
-                    "note": "latency/L2-bound integer path: ~570 dependent trie lookups per sentence vs ~250 B of "
-                            "compulsory HBM traffic (SURVEY 8d 'honest expectation')"}
+                    "note": "instruction-issue / dependent-lookup bound integer path: ~450 dependent trie lookups per "
+                            "sentence vs ~256 B of compulsory HBM traffic; DRAM traffic above the algorithmic bytes "
+                            "is the per-lane text + back-pointer slabs spilling out of L2 (DESIGN.md 5)"}
         cpu = None
         if not args.no_cpu:
             from oracle import oracle_py

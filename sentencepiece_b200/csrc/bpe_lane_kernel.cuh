@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(768, 1) encode_bpe_lane_kernel(const KModel M,
     ps = reinterpret_cast<float *>(a + kBpeWordSyms * 32 * 8) + lane;         // pair score
     uint8_t *slab = slabs + static_cast<size_t>(warp_global) * lane_slab_bytes(cap);
     c.text_w = reinterpret_cast<uint32_t *>(slab) + lane;
-    c.log = reinterpret_cast<uint32_t *>(slab) + static_cast<size_t>(cap / 4 + 4) * 32 + lane;
+    c.log = reinterpret_cast<uint32_t *>(slab) + static_cast<size_t>(cap / 4 + kLaneTextSlack) * 32 + lane;
     c.rs = nullptr;
     c.rb = nullptr;
     c.s_lead = s_tab;
@@ -70,8 +70,26 @@ __global__ void __launch_bounds__(768, 1) encode_bpe_lane_kernel(const KModel M,
   const uint2 *node2 = M.trie_node2;
   const uint32_t root = __ldg(&node2[0]).x;
   const bool bf = M.flags & kFlagByteFallback;
+  // 32-byte register window over the lane's text (words bw .. bw+7): a word's bytes are read many
+  // times (character split, every pair evaluation), so they must not go back to L2 each time
+  uint32_t bw = 0xFFFFFFF0u, t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0, t5 = 0, t6 = 0, t7 = 0;
+  auto load_window = [&](uint32_t k) {
+    bw = k >> 2;
+    const uint32_t *q = c.text_w + static_cast<size_t>(bw) * 32;
+    t0 = q[0]; t1 = q[32]; t2 = q[64]; t3 = q[96];
+    t4 = q[128]; t5 = q[160]; t6 = q[192]; t7 = q[224];
+  };
   auto text_byte = [&](uint32_t k) -> uint32_t {
-    return (c.text_w[static_cast<size_t>(k >> 2) * 32] >> ((k & 3u) * 8u)) & 0xFFu;
+    const uint32_t d = (k >> 2) - bw;
+    uint32_t w;
+    if (d < 8u) {
+      const uint32_t lo = (d & 2u) ? ((d & 1u) ? t3 : t2) : ((d & 1u) ? t1 : t0);
+      const uint32_t hi = (d & 2u) ? ((d & 1u) ? t7 : t6) : ((d & 1u) ? t5 : t4);
+      w = (d & 4u) ? hi : lo;
+    } else {
+      w = c.text_w[static_cast<size_t>(k >> 2) * 32];
+    }
+    return (w >> ((k & 3u) * 8u)) & 0xFFu;
   };
   // walks `len` bytes at text offset `off` from link word `l`; returns the node reached (and its
   // link word) or kBpeDead
@@ -114,6 +132,7 @@ __global__ void __launch_bounds__(768, 1) encode_bpe_lane_kernel(const KModel M,
       // -- split the word into characters (bpe_model.cc:110-120) and cache their trie nodes --
       uint32_t m = 0, q = p;
       bool first_sym = true;
+      if ((p >> 2) - bw >= 4u) load_window(p);  // keep at least 16 bytes of the word in registers
       while (q < n) {
         const uint32_t b0 = text_byte(q);
         uint32_t l = one_char_len(b0);

@@ -33,9 +33,10 @@ namespace spm_b200 {
 
 constexpr uint32_t kLaneUnk = 0x3FFFFFu;  // 22-bit trie-unit field: UNK piece
 
-// slab geometry: per warp [text words: cap/4 + 4][32] u32, then [log: cap + 4][32] u32
+// slab geometry: per warp [text words: cap/4 + 12][32] u32, then [log: cap + 4][32] u32
+constexpr uint32_t kLaneTextSlack = 12;  // window loads may run a few words past the text
 __host__ __device__ inline unsigned long long lane_slab_bytes(uint32_t cap) {
-  return (static_cast<unsigned long long>(cap / 4 + 4) + (cap + 4)) * 32ull * 4ull;
+  return (static_cast<unsigned long long>(cap / 4 + kLaneTextSlack) + (cap + 4)) * 32ull * 4ull;
 }
 // shared memory for the normalizer's fast-path tables
 constexpr uint32_t kLaneTableBytes = 32 + 4096 + 512 + 16;  // cm_lead[8] + cm_pair[1024] + cm_solo[128] + plain[4]
@@ -300,7 +301,7 @@ __global__ void __launch_bounds__(1024, 1) encode_unigram_lane_kernel(const KMod
     c.rb = reinterpret_cast<uint32_t *>(ring + R * 32 * 4) + lane;
     uint8_t *slab = slabs + static_cast<size_t>(warp_global) * lane_slab_bytes(cap);
     c.text_w = reinterpret_cast<uint32_t *>(slab) + lane;
-    c.log = reinterpret_cast<uint32_t *>(slab) + static_cast<size_t>(cap / 4 + 4) * 32 + lane;
+    c.log = reinterpret_cast<uint32_t *>(slab) + static_cast<size_t>(cap / 4 + kLaneTextSlack) * 32 + lane;
     c.s_lead = s_tab;
     c.s_pair = s_tab + 8;
     c.s_solo = reinterpret_cast<const int32_t *>(s_tab + 8 + 1024);
