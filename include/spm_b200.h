@@ -124,6 +124,35 @@ int spm_encode_ids_device(spm_engine *e, const char *d_bytes, const uint64_t *d_
                           uint64_t total_bytes, int32_t *d_ids, uint64_t ids_capacity,
                           uint64_t *d_id_offsets, uint64_t *total_ids, void *stream);
 
+/* ------------------------------------------------------------------------
+ * N-best and sampling (unigram models; BASELINE.json config 5).
+ *
+ * spm_nbest_encode replaces SentencePieceProcessor::NBestEncode(input, nbest_size, ids)
+ * (src/sentencepiece_processor.cc:653-676 -> unigram::Model::NBestEncode,
+ * src/unigram_model.cc:695-721): for every sentence up to nbest_size candidate id sequences in
+ * the reference's order (libstdc++ heap order among ties included) with their float scores.
+ * nbest_size is clamped to [1, 1024] like the reference; nbest_size <= 1 gives the Viterbi
+ * segmentation with score 0.  Candidate c of sentence i is
+ * ids[cand_offsets[i*K + c] .. cand_offsets[i*K + c + 1]) with K = the clamped nbest_size;
+ * n_cands[i] tells how many of the K slots are real. */
+int spm_nbest_encode(spm_engine *e, const char *bytes, const uint64_t *offsets, size_t n, int nbest_size,
+                     const int32_t **ids, const uint64_t **cand_offsets, const float **scores,
+                     const uint32_t **n_cands);
+
+/* sentencepiece::SetRandomGeneratorSeed (src/sentencepiece_processor.h:731) for this engine's
+ * std::mt19937; the engine draws for the sentences of a batch in order on one generator, which is
+ * what the reference does on one thread. */
+int spm_set_random_seed(spm_engine *e, uint32_t seed);
+
+/* Replaces SentencePieceProcessor::SampleEncode(input, nbest_size, alpha, ids)
+ * (src/sentencepiece_processor.cc:678-722) for nbest_size in [0, 512]: nbest_size of 0 or 1 is
+ * the plain Encode; otherwise the n-best list is computed on the GPU and one candidate is drawn
+ * with probability proportional to exp(alpha * score) exactly as the reference does
+ * (log-sum-exp in double, std::discrete_distribution on std::mt19937).  nbest_size < 0
+ * (forward-filtering/backward-sampling) and BPE-dropout are not on the accelerated path. */
+int spm_sample_encode_ids(spm_engine *e, const char *bytes, const uint64_t *offsets, size_t n, int nbest_size,
+                          float alpha, const int32_t **ids, const uint64_t **id_offsets);
+
 /* Pinned host memory helpers for callers that want zero staging copies. */
 void *spm_host_alloc(size_t bytes);
 void spm_host_free(void *p);

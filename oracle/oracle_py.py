@@ -177,6 +177,43 @@ class OracleModel:
     def model_encode(self, normalized):
         return self._enc(self.lib.oracle_model_encode, normalized)
 
+    def nbest_encode(self, s, nbest_size):
+        """-> (list of int32 id arrays, float32 scores) like SentencePieceProcessor::NBestEncode"""
+        L = self.lib
+        L.oracle_nbest_encode.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int,
+                                          ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p),
+                                          ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t)]
+        ids, co, sc, k = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_size_t()
+        rc = L.oracle_nbest_encode(self.h, s, len(s), nbest_size, ctypes.byref(ids), ctypes.byref(co), ctypes.byref(sc),
+                                   ctypes.byref(k))
+        if rc:
+            raise RuntimeError(f"oracle_nbest_encode rc={rc}")
+        kk = k.value
+        off = _u32(co, kk + 1)
+        allids = _i32(ids, int(off[kk]))
+        scores = np.ctypeslib.as_array(ctypes.cast(sc, ctypes.POINTER(ctypes.c_float)), (kk,)).copy()
+        for ptr in (ids, co, sc):
+            L.oracle_free(ptr)
+        return [allids[int(off[i]):int(off[i + 1])] for i in range(kk)], scores
+
+    def sample_encode_batch(self, buf, offs, nbest_size, alpha, seed):
+        L = self.lib
+        L.oracle_sample_encode_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
+                                                 ctypes.c_int, ctypes.c_float, ctypes.c_uint32,
+                                                 ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p]
+        n = len(offs) - 1
+        ido = np.zeros(n + 1, dtype=np.uint64)
+        ids = ctypes.c_void_p()
+        buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        offs = np.ascontiguousarray(offs, dtype=np.uint64)
+        rc = L.oracle_sample_encode_batch(self.h, buf.ctypes.data, offs.ctypes.data, n, nbest_size, alpha, seed,
+                                          ctypes.byref(ids), ido.ctypes.data)
+        if rc:
+            raise RuntimeError(f"oracle_sample_encode_batch failed at sentence {rc - 1}")
+        a = _i32(ids, int(ido[n]))
+        L.oracle_free(ids)
+        return a, ido
+
     def encode_batch(self, buf, offs):
         n = len(offs) - 1
         ido = np.zeros(n + 1, dtype=np.uint64)
@@ -269,6 +306,40 @@ class RefModel:
         self.lib.ref_free_buf(out)
         self.lib.ref_free_buf(n2o)
         return res, m
+
+    def nbest_encode(self, s, nbest_size):
+        L = self.lib
+        L.ref_nbest_encode.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int,
+                                       ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p),
+                                       ctypes.POINTER(ctypes.c_void_p)]
+        ids, co, sc = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+        k = L.ref_nbest_encode(self.h, s, len(s), nbest_size, ctypes.byref(ids), ctypes.byref(co), ctypes.byref(sc))
+        if k < 0:
+            raise RuntimeError("reference NBestEncode failed")
+        off = _u32(co, k + 1)
+        allids = _i32(ids, int(off[k]))
+        scores = np.ctypeslib.as_array(ctypes.cast(sc, ctypes.POINTER(ctypes.c_float)), (max(k, 1),))[:k].copy()
+        for ptr in (ids, co, sc):
+            L.ref_free_buf(ptr)
+        return [allids[int(off[i]):int(off[i + 1])] for i in range(k)], scores
+
+    def sample_encode_batch(self, buf, offs, nbest_size, alpha, seed):
+        L = self.lib
+        L.ref_sample_encode_ids.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
+                                            ctypes.c_int, ctypes.c_float, ctypes.c_uint, ctypes.POINTER(ctypes.c_void_p),
+                                            ctypes.c_void_p]
+        n = len(offs) - 1
+        ido = np.zeros(n + 1, dtype=np.uint64)
+        ids = ctypes.c_void_p()
+        buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        offs = np.ascontiguousarray(offs, dtype=np.uint64)
+        rc = L.ref_sample_encode_ids(self.h, buf.ctypes.data, offs.ctypes.data, n, nbest_size, alpha, seed,
+                                     ctypes.byref(ids), ido.ctypes.data)
+        if rc:
+            raise RuntimeError(f"reference SampleEncode failed at sentence {rc - 1}")
+        a = _i32(ids, int(ido[n]))
+        L.ref_free_buf(ids)
+        return a, ido
 
     def encode_pieces(self, s):
         out = ctypes.c_void_p()

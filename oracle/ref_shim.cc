@@ -172,3 +172,61 @@ int ref_piece_size(void *h) {
 }
 
 }  // extern "C"
+
+// ---- n-best / sampling (config 5) -------------------------------------------------
+#include "sentencepiece.pb.h"
+
+extern "C" {
+
+// NBestEncode for one sentence (src/sentencepiece_processor.cc:653-676).  Outputs (malloc'ed):
+// ids of all candidates packed, cand_off[k+1], scores[k]; returns k (candidates) or -1.
+int ref_nbest_encode(void *h, const char *s, size_t len, int nbest_size, int32_t **ids_out, uint32_t **cand_off_out,
+                     float **scores_out) {
+  auto *sp = static_cast<SentencePieceProcessor *>(h);
+  sentencepiece::NBestSentencePieceText nb;
+  if (!sp->NBestEncode(absl::string_view(s, len), nbest_size, &nb).ok()) return -1;
+  const int k = nb.nbests_size();
+  size_t total = 0;
+  for (int i = 0; i < k; ++i) total += nb.nbests(i).pieces_size();
+  int32_t *ids = static_cast<int32_t *>(malloc(sizeof(int32_t) * (total ? total : 1)));
+  uint32_t *off = static_cast<uint32_t *>(malloc(sizeof(uint32_t) * (k + 1)));
+  float *sc = static_cast<float *>(malloc(sizeof(float) * (k ? k : 1)));
+  size_t p = 0;
+  for (int i = 0; i < k; ++i) {
+    off[i] = static_cast<uint32_t>(p);
+    sc[i] = nb.nbests(i).score();
+    for (const auto &piece : nb.nbests(i).pieces()) ids[p++] = piece.id();
+  }
+  off[k] = static_cast<uint32_t>(p);
+  *ids_out = ids; *cand_off_out = off; *scores_out = sc;
+  return k;
+}
+
+// SampleEncode(input, nbest_size, alpha) over a packed batch, sequentially on THIS thread, after
+// seeding the thread's generator state deterministically: the reference seeds its thread_local
+// mt19937 from the global seed on first use in a thread (src/util.cc:192-205), so the batch is run
+// on a fresh std::thread.  Outputs like ref_encode_ids.
+int ref_sample_encode_ids(void *h, const char *bytes, const uint64_t *offs, size_t n, int nbest_size, float alpha,
+                          unsigned int seed, int32_t **ids_out, uint64_t *id_offsets) {
+  auto *sp = static_cast<SentencePieceProcessor *>(h);
+  std::vector<std::vector<int>> outs(n);
+  int failed = 0;
+  sentencepiece::SetRandomGeneratorSeed(seed);
+  std::thread t([&]() {
+    for (size_t i = 0; i < n; ++i)
+      if (!sp->SampleEncode(absl::string_view(bytes + offs[i], offs[i + 1] - offs[i]), nbest_size, alpha, &outs[i]).ok())
+        failed = static_cast<int>(i + 1);
+  });
+  t.join();
+  if (failed) return failed;
+  uint64_t total = 0;
+  for (size_t i = 0; i < n; ++i) { id_offsets[i] = total; total += outs[i].size(); }
+  id_offsets[n] = total;
+  int32_t *ids = static_cast<int32_t *>(malloc(sizeof(int32_t) * (total ? total : 1)));
+  for (size_t i = 0; i < n; ++i)
+    if (!outs[i].empty()) memcpy(ids + id_offsets[i], outs[i].data(), sizeof(int32_t) * outs[i].size());
+  *ids_out = ids;
+  return 0;
+}
+
+}  // extern "C"

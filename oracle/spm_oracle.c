@@ -717,3 +717,303 @@ int oracle_encode_batch(const oracle_model *m, const char *bytes, const uint64_t
   *ids_out = all;
   return 0;
 }
+
+/* =========================================================== n-best + sampling == */
+
+typedef struct {
+  int32_t pos, length;     /* in Unicode characters (Lattice::Node, unigram_model.h:38-49) */
+  int32_t id;
+  float score, backtrace_score;
+  uint32_t bbeg, bend;     /* byte span in the normalized text */
+} lnode;
+typedef struct { int32_t *a; size_t n, cap; } ivec;
+static void iv_push(ivec *v, int32_t x) {
+  if (v->n == v->cap) { v->cap = v->cap ? v->cap * 2 : 8; v->a = realloc(v->a, v->cap * sizeof(int32_t)); }
+  v->a[v->n++] = x;
+}
+typedef struct { int32_t node, next; float fx, gx; } hyp_t;
+
+/* std::push_heap / std::pop_heap on indices ordered by fx with comp(a,b) = a.fx < b.fx
+ * (/usr/include/c++/13/bits/stl_heap.h:135-148, 224-267) */
+static void heap_push(int32_t *h, size_t *n, const hyp_t *pool, int32_t v) {
+  size_t hole = (*n)++;
+  while (hole > 0) {
+    const size_t parent = (hole - 1) / 2;
+    if (!(pool[h[parent]].fx < pool[v].fx)) break; /* equal keys do not move up */
+    h[hole] = h[parent];
+    hole = parent;
+  }
+  h[hole] = v;
+}
+static int32_t heap_pop(int32_t *h, size_t *n, const hyp_t *pool) {
+  /* __pop_heap: result = first; value = last; __adjust_heap(first, 0, len-1, value) */
+  const int32_t top = h[0];
+  const size_t len = --(*n);
+  if (len == 0) return top;
+  const int32_t value = h[len];
+  size_t hole = 0, child = 0;
+  while (child < (len - 1) / 2) {
+    child = 2 * (child + 1);
+    if (pool[h[child]].fx < pool[h[child - 1]].fx) child--;
+    h[hole] = h[child];
+    hole = child;
+  }
+  if ((len & 1) == 0 && child == (len - 2) / 2) {
+    child = 2 * (child + 1);
+    h[hole] = h[child - 1];
+    hole = child - 1;
+  }
+  /* __push_heap(first, hole, 0, value) */
+  while (hole > 0) {
+    const size_t parent = (hole - 1) / 2;
+    if (!(pool[h[parent]].fx < pool[value].fx)) break;
+    h[hole] = h[parent];
+    hole = parent;
+  }
+  h[hole] = value;
+  return top;
+}
+
+/* id path of PopulateSentencePieceText over (byte_len, id) pieces of one candidate */
+static void emit_candidate(const oracle_model *m, const unsigned char *norm, const uint32_t *plen, const int32_t *pid,
+                           size_t np, outv *o) {
+  size_t consumed = 0;
+  int prev_unk = 0;
+  for (size_t k = 0; k < np; ++k) {
+    const int is_unk = pid[k] == m->unk_id;
+    if (is_unk && m->byte_fallback) {
+      for (uint32_t i = 0; i < plen[k]; ++i) out_push(o, m->byte_to_id[norm[consumed + i]], (uint32_t)(consumed + i + 1));
+    } else if (prev_unk && is_unk) {
+      o->ends[o->n - 1] = (uint32_t)(consumed + plen[k]);
+    } else {
+      out_push(o, pid[k], (uint32_t)(consumed + plen[k]));
+    }
+    consumed += plen[k];
+    prev_unk = is_unk;
+  }
+}
+
+int oracle_nbest_encode(const oracle_model *m, const char *in, size_t len, int nbest_size, int32_t **ids_out,
+                        uint32_t **cand_off_out, float **scores_out, size_t *k_out) {
+  char *norm_; size_t nlen; uint64_t *n2o; size_t n2o_len;
+  *ids_out = NULL; *cand_off_out = NULL; *scores_out = NULL; *k_out = 0;
+  if (m->model_type != ORACLE_UNIGRAM) return 2; /* IsNBestEncodeAvailable, sentencepiece_processor.cc:662 */
+  if (oracle_normalize(m, in, len, &norm_, &nlen, &n2o, &n2o_len)) return 1;
+  free(n2o);
+  const unsigned char *norm = (const unsigned char *)norm_;
+  outv all = {0};
+  uint32_t *cand_off = NULL; float *scores = NULL; size_t K = 0;
+  /* Model::NBestEncode, unigram_model.cc:695-721 */
+  if (nlen == 0) {                       /* {{{}, 0.0}} */
+    cand_off = malloc(2 * sizeof(uint32_t)); scores = malloc(sizeof(float));
+    cand_off[0] = cand_off[1] = 0; scores[0] = 0.f; K = 1;
+    goto done;
+  }
+  if (nbest_size > 1024) nbest_size = 1024;
+  if (nbest_size < 1) nbest_size = 1;
+  if (nbest_size <= 1) {                 /* Encode(normalized), score 0.0 */
+    int32_t *ids; uint32_t *ends; size_t n;
+    unigram_encode(m, norm, nlen, &ids, &ends, &n);
+    uint32_t *pl = malloc(sizeof(uint32_t) * (n ? n : 1));
+    for (size_t i = 0; i < n; ++i) pl[i] = ends[i] - (i ? ends[i - 1] : 0);
+    emit_candidate(m, norm, pl, ids, n, &all);
+    cand_off = malloc(2 * sizeof(uint32_t)); scores = malloc(sizeof(float));
+    cand_off[0] = 0; cand_off[1] = (uint32_t)all.n; scores[0] = 0.f; K = 1;
+    free(ids); free(ends); free(pl);
+    goto done;
+  }
+  {
+    /* Lattice::SetSentence, :113-146: character positions */
+    uint32_t *surf = malloc(sizeof(uint32_t) * (nlen + 2));
+    int L = 0;
+    for (size_t p = 0; p < nlen;) {
+      size_t mb = one_char_len(norm[p]);
+      if (mb > nlen - p) mb = nlen - p;
+      surf[L++] = (uint32_t)p;
+      p += mb;
+    }
+    surf[L] = (uint32_t)nlen;
+    size_t ncap = 64, nn = 0;
+    lnode *nodes = malloc(ncap * sizeof(lnode));
+    ivec *begin_nodes = calloc((size_t)L + 1, sizeof(ivec)), *end_nodes = calloc((size_t)L + 1, sizeof(ivec));
+#define NEW_NODE() (nn == ncap ? (nodes = realloc(nodes, (ncap *= 2) * sizeof(lnode)), &nodes[nn++]) : &nodes[nn++])
+    { lnode *bos = NEW_NODE(); memset(bos, 0, sizeof *bos); bos->id = -1; bos->pos = 0; iv_push(&end_nodes[0], 0); }
+    { lnode *eos = NEW_NODE(); memset(eos, 0, sizeof *eos); eos->id = -1; eos->pos = L; iv_push(&begin_nodes[L], 1); }
+    /* Model::PopulateNodes, :547-596 */
+    const float unk_score = m->min_score - 10.0f;
+    for (int bp = 0; bp < L; ++bp) {
+      int has_single = 0;
+      uint32_t node = 0;
+      for (size_t kpos = surf[bp]; kpos < nlen; ++kpos) {     /* commonPrefixSearch: results by length */
+        const int32_t c = ht_child(&m->pieces, node, norm[kpos]);
+        if (c < 0) break;
+        node = (uint32_t)c;
+        const int32_t id = m->pieces.value[node];
+        if (id < 0) continue;
+        const uint32_t endb = (uint32_t)kpos + 1;
+        int length = 0;                                       /* get_chars_length, :548-552 */
+        { int pos = bp; while (surf[pos] < endb) ++pos; length = pos - bp; }
+        if (m->types[id] == ORACLE_UNUSED) continue;
+        lnode *nd = NEW_NODE();
+        memset(nd, 0, sizeof *nd);
+        nd->pos = bp; nd->length = length; nd->id = id;
+        nd->bbeg = surf[bp]; nd->bend = surf[bp + length];
+        nd->score = m->types[id] == ORACLE_USER_DEFINED ? (float)((double)((float)length * m->max_score) - 0.1)
+                                                         : m->scores[id];
+        iv_push(&begin_nodes[bp], (int32_t)(nn - 1));
+        iv_push(&end_nodes[bp + length], (int32_t)(nn - 1));
+        if (!has_single && length == 1) has_single = 1;
+      }
+      if (!has_single) {
+        lnode *nd = NEW_NODE();
+        memset(nd, 0, sizeof *nd);
+        nd->pos = bp; nd->length = 1; nd->id = m->unk_id; nd->score = unk_score;
+        nd->bbeg = surf[bp]; nd->bend = surf[bp + 1];
+        iv_push(&begin_nodes[bp], (int32_t)(nn - 1));
+        iv_push(&end_nodes[bp + 1], (int32_t)(nn - 1));
+      }
+    }
+    /* Lattice::Viterbi, :161-198 (only the backtrace scores are needed) */
+    for (int pos = 0; pos <= L; ++pos)
+      for (size_t r = 0; r < begin_nodes[pos].n; ++r) {
+        lnode *rn = &nodes[begin_nodes[pos].a[r]];
+        float best = 0.f; int have = 0;
+        for (size_t q = 0; q < end_nodes[pos].n; ++q) {
+          const float sc = nodes[end_nodes[pos].a[q]].backtrace_score + rn->score;
+          if (!have || sc > best) { best = sc; have = 1; }
+        }
+        rn->backtrace_score = best;
+      }
+    /* Lattice::NBest, :345-509 (sample == false) */
+    size_t pcap = 1024, pn = 0, hcap = 1024, hn = 0;
+    hyp_t *pool = malloc(pcap * sizeof(hyp_t));
+    int32_t *heap = malloc(hcap * sizeof(int32_t));
+    pool[pn].node = 1; pool[pn].next = -1; pool[pn].gx = 0.f; pool[pn].fx = nodes[1].backtrace_score; pn++;
+    heap_push(heap, &hn, pool, 0);
+    cand_off = malloc(sizeof(uint32_t) * ((size_t)nbest_size + 1));
+    scores = malloc(sizeof(float) * (size_t)nbest_size);
+    cand_off[0] = 0;
+    uint32_t *pl = malloc(sizeof(uint32_t) * ((size_t)L + 1));
+    int32_t *pi = malloc(sizeof(int32_t) * ((size_t)L + 1));
+    while (hn) {
+      const int32_t top = heap_pop(heap, &hn, pool);
+      const int32_t node = pool[top].node;
+      if (node == 0) {                                         /* reached BOS */
+        size_t np = 0;
+        for (int32_t h = pool[top].next; pool[h].next != -1; h = pool[h].next) {
+          pl[np] = nodes[pool[h].node].bend - nodes[pool[h].node].bbeg;
+          pi[np] = nodes[pool[h].node].id;
+          ++np;
+        }
+        emit_candidate(m, norm, pl, pi, np, &all);
+        scores[K] = pool[top].fx;
+        cand_off[++K] = (uint32_t)all.n;
+        if (K == (size_t)nbest_size) break;
+        continue;
+      }
+      const ivec *en = &end_nodes[nodes[node].pos];
+      for (size_t q = 0; q < en->n; ++q) {
+        const lnode *ln = &nodes[en->a[q]];
+        if (pn == pcap) { pcap *= 2; pool = realloc(pool, pcap * sizeof(hyp_t)); }
+        pool[pn].node = en->a[q];
+        pool[pn].gx = ln->score + pool[top].gx;
+        pool[pn].fx = ln->backtrace_score + pool[top].gx;
+        pool[pn].next = top;
+        if (hn == hcap) { hcap *= 2; heap = realloc(heap, hcap * sizeof(int32_t)); }
+        heap_push(heap, &hn, pool, (int32_t)pn);
+        pn++;
+      }
+      if (hn >= 10000) {                                       /* agenda shrink, :481-505 */
+        int size = nbest_size * 10 < 512 ? nbest_size * 10 : 512;
+        int32_t *keep = malloc(sizeof(int32_t) * (size_t)size);
+        for (int i = 0; i < size; ++i) keep[i] = heap_pop(heap, &hn, pool);
+        /* pushing in descending order into an empty heap leaves them in that order */
+        hn = 0;
+        for (int i = 0; i < size; ++i) heap_push(heap, &hn, pool, keep[i]);
+        free(keep);
+      }
+    }
+    free(pl); free(pi); free(pool); free(heap);
+    for (int i = 0; i <= L; ++i) { free(begin_nodes[i].a); free(end_nodes[i].a); }
+    free(begin_nodes); free(end_nodes); free(nodes); free(surf);
+#undef NEW_NODE
+  }
+done:
+  free(norm_);
+  free(all.ends);
+  *ids_out = all.ids ? all.ids : malloc(4);
+  *cand_off_out = cand_off; *scores_out = scores; *k_out = K;
+  return 0;
+}
+
+/* std::mt19937 (MT19937, 32-bit) */
+void oracle_mt_seed(oracle_mt19937 *g, uint32_t seed) {
+  g->mt[0] = seed;
+  for (int i = 1; i < 624; ++i) g->mt[i] = 1812433253u * (g->mt[i - 1] ^ (g->mt[i - 1] >> 30)) + (uint32_t)i;
+  g->idx = 624;
+}
+static uint32_t mt_next(oracle_mt19937 *g) {
+  if (g->idx >= 624) {
+    for (int i = 0; i < 624; ++i) {
+      const uint32_t y = (g->mt[i] & 0x80000000u) | (g->mt[(i + 1) % 624] & 0x7FFFFFFFu);
+      g->mt[i] = g->mt[(i + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908B0DFu : 0u);
+    }
+    g->idx = 0;
+  }
+  uint32_t y = g->mt[g->idx++];
+  y ^= y >> 11; y ^= (y << 7) & 0x9D2C5680u; y ^= (y << 15) & 0xEFC60000u; y ^= y >> 18;
+  return y;
+}
+
+/* sentencepiece_processor.cc:703-718 + libstdc++ discrete_distribution (bits/random.tcc):
+ * probabilities normalised by their sum, cumulative sums with the last forced to 1.0,
+ * p = generate_canonical<double,53>(mt) = (x0 + x1 * 2^32) / 2^64 in double arithmetic,
+ * result = lower_bound(cp, p). */
+int oracle_sample_pick(oracle_mt19937 *g, const float *scores, size_t k, float alpha) {
+  if (k < 2) return 0; /* _M_initialize clears the table: operator() returns 0 without drawing */
+  double *lp = malloc(sizeof(double) * k), *cp = malloc(sizeof(double) * k);
+  for (size_t i = 0; i < k; ++i) lp[i] = (double)(alpha * scores[i]); /* float product widened */
+  double Z = lp[0];                                                   /* log_domain::LogSum, util.cc:278-294 */
+  for (size_t i = 1; i < k; ++i) {
+    double xa = Z, xb = lp[i];
+    if (xa > xb) { const double t = xa; xa = xb; xb = t; }
+    Z = xb + log1p(exp(xa - xb));
+  }
+  double sum = 0.0;
+  for (size_t i = 0; i < k; ++i) { lp[i] = exp(lp[i] - Z); sum += lp[i]; }
+  double run = 0.0;
+  for (size_t i = 0; i < k; ++i) { run += lp[i] / sum; cp[i] = run; }
+  cp[k - 1] = 1.0;
+  const double x0 = (double)mt_next(g), x1 = (double)mt_next(g);
+  double p = (x0 + x1 * 4294967296.0) / 18446744073709551616.0;
+  if (p >= 1.0) p = nextafter(1.0, 0.0);
+  size_t lo = 0, hi = k;                                              /* std::lower_bound */
+  while (lo < hi) { const size_t mid = lo + (hi - lo) / 2; if (cp[mid] < p) lo = mid + 1; else hi = mid; }
+  free(lp); free(cp);
+  return (int)lo;
+}
+
+int oracle_sample_encode_batch(const oracle_model *m, const char *bytes, const uint64_t *offs, size_t n, int nbest_size,
+                               float alpha, uint32_t seed, int32_t **ids_out, uint64_t *id_offsets) {
+  oracle_mt19937 g;
+  oracle_mt_seed(&g, seed);
+  size_t cap = 1024, total = 0;
+  int32_t *all = malloc(cap * sizeof(int32_t));
+  for (size_t i = 0; i < n; ++i) {
+    int32_t *ids; uint32_t *co; float *sc; size_t k;
+    if (oracle_nbest_encode(m, bytes + offs[i], (size_t)(offs[i + 1] - offs[i]), nbest_size, &ids, &co, &sc, &k)) {
+      free(all);
+      return (int)(i + 1);
+    }
+    const int pick = oracle_sample_pick(&g, sc, k, alpha);
+    const size_t cnt = co[pick + 1] - co[pick];
+    id_offsets[i] = total;
+    if (total + cnt > cap) { while (total + cnt > cap) cap *= 2; all = realloc(all, cap * sizeof(int32_t)); }
+    if (cnt) memcpy(all + total, ids + co[pick], cnt * sizeof(int32_t));
+    total += cnt;
+    free(ids); free(co); free(sc);
+  }
+  id_offsets[n] = total;
+  *ids_out = all;
+  return 0;
+}

@@ -75,6 +75,26 @@ int oracle_encode(const oracle_model *m, const char *in, size_t len, int32_t **i
 int oracle_encode_batch(const oracle_model *m, const char *bytes, const uint64_t *offs, size_t n,
                         int32_t **ids, uint64_t *id_offsets);
 
+/* ---- config 5: n-best + sampling ----
+ * SentencePieceProcessor::NBestEncode (src/sentencepiece_processor.cc:653-676) =
+ * Normalize -> unigram::Model::NBestEncode (src/unigram_model.cc:695-721: Lattice::SetSentence
+ * :113-146, Model::PopulateNodes :547-596, Lattice::Viterbi :161-198, Lattice::NBest :345-509 with
+ * libstdc++'s heap order) -> PopulateSentencePieceText per candidate.
+ * Outputs (malloc'ed): ids of all candidates packed, cand_off[k+1], scores[k]; *k = candidates. */
+int oracle_nbest_encode(const oracle_model *m, const char *in, size_t len, int nbest_size, int32_t **ids,
+                        uint32_t **cand_off, float **scores, size_t *k);
+
+/* std::mt19937 + std::discrete_distribution<int> exactly as libstdc++ runs them in
+ * SentencePieceProcessor::SampleEncode (src/sentencepiece_processor.cc:699-719). */
+typedef struct { uint32_t mt[624]; int idx; } oracle_mt19937;
+void oracle_mt_seed(oracle_mt19937 *g, uint32_t seed);
+/* index drawn for candidate scores[k] and `alpha`; consumes two 32-bit draws iff k >= 2 */
+int oracle_sample_pick(oracle_mt19937 *g, const float *scores, size_t k, float alpha);
+
+/* SampleEncode(input, nbest_size > 1, alpha) over a packed batch in order on one generator. */
+int oracle_sample_encode_batch(const oracle_model *m, const char *bytes, const uint64_t *offs, size_t n, int nbest_size,
+                               float alpha, uint32_t seed, int32_t **ids, uint64_t *id_offsets);
+
 void oracle_free(void *p);
 
 #ifdef __cplusplus

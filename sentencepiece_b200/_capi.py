@@ -13,7 +13,8 @@ LIB_PATH = os.path.join(_HERE, "lib", "libspm_b200.so")
 EXPORTS = [
     "spm_engine_create", "spm_engine_create_from_serialized", "spm_engine_destroy", "spm_engine_set_types",
     "spm_last_error", "spm_encode_ids", "spm_encode_spans", "spm_encode_ids_device", "spm_host_alloc",
-    "spm_host_free", "spm_engine_get_info", "spm_engine_set_tuning",
+    "spm_host_free", "spm_engine_get_info", "spm_engine_set_tuning", "spm_nbest_encode", "spm_set_random_seed",
+    "spm_sample_encode_ids",
 ]
 
 
@@ -68,5 +69,8 @@ def load():
     L.spm_host_free.restype = None
     L.spm_engine_get_info.argtypes = [vp, P(EngineInfo)]
     L.spm_engine_set_tuning.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    L.spm_nbest_encode.argtypes = [vp, vp, vp, sz, ctypes.c_int, P(vp), P(vp), P(vp), P(vp)]
+    L.spm_set_random_seed.argtypes = [vp, ctypes.c_uint32]
+    L.spm_sample_encode_ids.argtypes = [vp, vp, vp, sz, ctypes.c_int, ctypes.c_float, P(vp), P(vp)]
     _lib = L
     return L

@@ -17,6 +17,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <random>
+#include <thread>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -28,6 +30,7 @@
 #include "kernels.cuh"
 #include "lane_kernel.cuh"
 #include "model_reader.h"
+#include "nbest_kernel.cuh"
 #include "trie_builder.h"
 #include "unigram_warp.cuh"
 
@@ -162,6 +165,16 @@ struct spm_engine {
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
   size_t pipeline_min_sentences = 300000, pipeline_chunk_sentences = 65536;
+  // n-best / sampling
+  DevBuf<uint8_t> d_nb_scratch;
+  DevBuf<unsigned long long> d_cand_start, d_cand_offsets;
+  DevBuf<uint32_t> d_cand_count, d_n_cands, d_picks;
+  DevBuf<float> d_cand_score;
+  PinBuf<float> h_cand_score;
+  PinBuf<uint32_t> h_n_cands, h_picks;
+  PinBuf<uint64_t> h_cand_offsets;
+  std::mt19937 rng{5489u};
+  int run_nbest(const char *bytes, const uint64_t *offsets, size_t n, uint32_t nbest, uint64_t *tmp_total);
 
   // stats of the last call
   uint64_t last_launches = 0, last_h2d = 0, last_d2h = 0, last_deferred = 0;
@@ -469,6 +482,7 @@ int spm_engine::configure_kernel_attrs() {
   CUDA_TRY(set_smem(encode_unigram_long_kernel<true>, mx));
   CUDA_TRY(set_smem(encode_unigram_lane_kernel, mx));
   CUDA_TRY(set_smem(encode_bpe_lane_kernel, mx));
+  CUDA_TRY(set_smem(nbest_lane_kernel, mx));
   CUDA_TRY(set_smem(encode_unigram_warp_kernel<512>, mx));
   CUDA_TRY(set_smem(encode_unigram_warp_kernel<1024>, mx));
   CUDA_TRY(set_smem(encode_bpe_kernel<false>, mx));
@@ -858,6 +872,77 @@ int spm_engine::encode_host_pipelined(const char *bytes, const uint64_t *offsets
   return SPM_OK;
 }
 
+// ---- n-best (K5): lattice + A* per sentence on the GPU; leaves candidates in the temporary buffers ----
+int spm_engine::run_nbest(const char *bytes, const uint64_t *offsets, size_t n, uint32_t nbest, uint64_t *tmp_total) {
+  cudaStream_t st = stream;
+  const uint64_t base = offsets[0];
+  const uint64_t total_bytes = offsets[n] - base;
+  CUDA_TRY(d_bytes.ensure(total_bytes + 64));
+  CUDA_TRY(d_offsets.ensure(n + 1));
+  if (total_bytes) CUDA_TRY(cudaMemcpyAsync(d_bytes.p, bytes + base, total_bytes, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(d_offsets.p, offsets, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+  last_h2d = total_bytes + (n + 1) * sizeof(uint64_t);
+  NbestGeom G{};
+  G.cap = lane_cap;
+  G.node_cap = std::min<uint32_t>(65535u, 4 * lane_cap + 64);
+  G.hyp_cap = 16384 + nbest * 96;
+  G.heap_cap = 10000 + 1024 + 512;
+  const int warps_per_cta = 4;
+  const size_t warps_total = static_cast<size_t>(sm_count) * warps_per_cta;
+  CUDA_TRY(d_lane_slabs.ensure(warps_total * lane_slab_bytes(lane_cap) + 256));
+  CUDA_TRY(d_nb_scratch.ensure(warps_total * 32 * nbest_lane_bytes(G) + 256));
+  const size_t nc = n * static_cast<size_t>(nbest);
+  CUDA_TRY(d_cand_start.ensure(nc));
+  CUDA_TRY(d_cand_count.ensure(nc));
+  CUDA_TRY(d_cand_score.ensure(nc));
+  CUDA_TRY(d_n_cands.ensure(n));
+  CUDA_TRY(d_ctrl32.ensure(16));
+  CUDA_TRY(d_ctrl64.ensure(4));
+  CUDA_TRY(h_ctrl32.ensure(16));
+  CUDA_TRY(h_ctrl64.ensure(4));
+  // candidates: at most one id per normalized byte each; start from 2 ids per input byte per 8 candidates
+  unsigned long long tmp_cap = std::max<unsigned long long>(1u << 20, total_bytes * nbest / 3 + 64ull * n);
+  for (int attempt = 0; attempt < 3; ++attempt) {
+    CUDA_TRY(d_tmp_ids.ensure(tmp_cap));
+    CUDA_TRY(cudaMemsetAsync(d_ctrl32.p, 0, 16 * sizeof(uint32_t), st));
+    CUDA_TRY(cudaMemsetAsync(d_ctrl64.p, 0, 4 * sizeof(unsigned long long), st));
+    KBatch B{};
+    B.bytes = d_bytes.p - base;
+    B.offsets = d_offsets.p;
+    B.n = static_cast<uint32_t>(n);
+    B.work_counter = d_ctrl32.p + 4;
+    B.status = d_ctrl32.p;
+    NbestOut O{};
+    O.tmp_ids = d_tmp_ids.p;
+    O.tmp_cap = tmp_cap;
+    O.cursor = d_ctrl64.p;
+    O.cand_start = d_cand_start.p;
+    O.cand_count = d_cand_count.p;
+    O.cand_score = d_cand_score.p;
+    O.n_cands = d_n_cands.p;
+    O.status = d_ctrl32.p;
+    CUDA_TRY(cudaEventRecord(ev[0], st));
+    nbest_lane_kernel<<<sm_count, warps_per_cta * 32, kLaneTableBytes, st>>>(km, B, O, d_lane_slabs.p, d_nb_scratch.p, G, nbest);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(ev[1], st));
+    ++last_launches;
+    CUDA_TRY(cudaMemcpyAsync(h_ctrl32.p, d_ctrl32.p, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(h_ctrl64.p, d_ctrl64.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (h_ctrl32.p[3]) {
+      set_error("n-best: a sentence exceeds the device path's capacity (normalized length > " + std::to_string(lane_cap) +
+                " bytes, lattice or hypothesis pool too large)");
+      return SPM_ERR_UNSUPPORTED;
+    }
+    if (h_ctrl32.p[1]) { set_error("n-best: internal consistency check failed"); return SPM_ERR_ENCODE; }
+    if (h_ctrl32.p[2]) { tmp_cap = h_ctrl64.p[0] + 1024; continue; }
+    *tmp_total = h_ctrl64.p[0];
+    return SPM_OK;
+  }
+  set_error("n-best: temporary buffer overflow persisted");
+  return SPM_ERR_CAPACITY;
+}
+
 // ---------------------------------------------------------------- C ABI ----
 
 extern "C" {
@@ -951,6 +1036,9 @@ void spm_engine_destroy(spm_engine *e) {
   e->d_long_off.release();
   e->d_lane_slabs.release();
   e->d_node2.release();
+  e->d_nb_scratch.release(); e->d_cand_start.release(); e->d_cand_offsets.release(); e->d_cand_count.release();
+  e->d_n_cands.release(); e->d_picks.release(); e->d_cand_score.release(); e->h_cand_score.release();
+  e->h_n_cands.release(); e->h_picks.release(); e->h_cand_offsets.release();
   for (int k = 0; k < 2; ++k) {
     e->p_bytes[k].release(); e->p_offsets[k].release(); e->p_ids[k].release(); e->p_id_offsets[k].release();
     if (e->ev_in[k]) cudaEventDestroy(e->ev_in[k]);
@@ -1135,6 +1223,185 @@ int spm_encode_ids(spm_engine *e, const char *bytes, const uint64_t *offsets, si
     return e->encode_host_pipelined(bytes, offsets, n, ids, id_offsets);
   }
   return encode_host(e, bytes, offsets, n, false, ids, nullptr, id_offsets, nullptr, nullptr, nullptr);
+}
+
+static int nbest_args_ok(spm_engine *e, const char *bytes, const uint64_t *offsets, size_t n) {
+  if (e->model.model_type != SPM_UNIGRAM) {
+    e->set_error("NBestEncode is not available for the current model.");  // sentencepiece_processor.cc:662-663
+    return SPM_ERR_UNSUPPORTED;
+  }
+  if (!offsets || (n && !bytes && offsets[n] != offsets[0]) || n >= 0x7FFFFFF0ull) { e->set_error("bad argument"); return SPM_ERR_ARG; }
+  for (size_t i = 0; i < n; ++i)
+    if (offsets[i + 1] < offsets[i]) { e->set_error("offsets must be non-decreasing"); return SPM_ERR_ARG; }
+  if (e->trie.max_key_len > 255) { e->set_error("pieces too long for the n-best device path"); return SPM_ERR_UNSUPPORTED; }
+  return SPM_OK;
+}
+
+int spm_set_random_seed(spm_engine *e, uint32_t seed) {
+  if (!e) return SPM_ERR_ARG;
+  std::lock_guard<std::mutex> lk(e->mu);
+  e->rng.seed(seed);
+  return SPM_OK;
+}
+
+int spm_nbest_encode(spm_engine *e, const char *bytes, const uint64_t *offsets, size_t n, int nbest_size,
+                     const int32_t **ids, const uint64_t **cand_offsets, const float **scores, const uint32_t **n_cands) {
+  if (!e || !ids || !cand_offsets || !scores || !n_cands) return SPM_ERR_ARG;
+  std::lock_guard<std::mutex> lk(e->mu);
+  auto set_error = [&](const std::string &m) { e->set_error(m); };
+  { const int rc = nbest_args_ok(e, bytes, offsets, n); if (rc) return rc; }
+  CUDA_TRY(cudaSetDevice(e->device));
+  const uint32_t K = static_cast<uint32_t>(std::max(1, std::min(nbest_size, 1024)));  // unigram_model.cc:701
+  cudaStream_t st = e->stream;
+  const size_t nc = n * static_cast<size_t>(K);
+  CUDA_TRY(e->h_cand_offsets.ensure(nc + 1));
+  CUDA_TRY(e->h_cand_score.ensure(nc + 1));
+  CUDA_TRY(e->h_n_cands.ensure(n + 1));
+  CUDA_TRY(e->h_ids.ensure(1));
+  *ids = e->h_ids.p; *cand_offsets = e->h_cand_offsets.p; *scores = e->h_cand_score.p; *n_cands = e->h_n_cands.p;
+  e->h_cand_offsets.p[0] = 0;
+  if (n == 0) return SPM_OK;
+  e->last_launches = 0;
+  if (K == 1) {
+    // nbest_size <= 1: {Encode(normalized), 0.0} (unigram_model.cc:703-705)
+    const int32_t *pid; const uint64_t *poff;
+    e->mu.unlock();
+    const int rc = spm_encode_ids(e, bytes, offsets, n, &pid, &poff);
+    e->mu.lock();
+    if (rc) return rc;
+    for (size_t i = 0; i <= n; ++i) e->h_cand_offsets.p[i] = poff[i];
+    for (size_t i = 0; i < n; ++i) { e->h_cand_score.p[i] = 0.f; e->h_n_cands.p[i] = 1; }
+    *ids = pid;
+    return SPM_OK;
+  }
+  uint64_t tmp_total = 0;
+  { const int rc = e->run_nbest(bytes, offsets, n, K, &tmp_total); if (rc) return rc; }
+  // candidate-major compaction: the shared scan + gather over n*K counts
+  const uint32_t nc32 = static_cast<uint32_t>(nc);
+  const uint32_t nb = (nc32 + kScanChunk - 1) / kScanChunk;
+  CUDA_TRY(e->d_block_sums.ensure(nb + 1));
+  CUDA_TRY(e->d_cand_offsets.ensure(nc + 1));
+  CUDA_TRY(e->d_ids.ensure(tmp_total + 1));
+  scan_block_sums_kernel<<<nb, 256, 0, st>>>(e->d_cand_count.p, nc32, e->d_block_sums.p, 0);
+  scan_block_prefix_kernel<<<1, 1024, 0, st>>>(e->d_block_sums.p, nb, e->d_ctrl64.p + 2);
+  scan_write_gather_kernel<int32_t><<<nb, 256, 0, st>>>(e->d_cand_count.p, nc32, e->d_block_sums.p, e->d_cand_offsets.p,
+                                                        e->d_cand_start.p, e->d_tmp_ids.p, e->d_ids.p, nullptr, nullptr,
+                                                        e->d_ids.cap, 0, 0ull);
+  CUDA_TRY(cudaGetLastError());
+  e->last_launches += 3;
+  CUDA_TRY(e->h_ids.ensure(tmp_total + 1));
+  if (tmp_total) CUDA_TRY(cudaMemcpyAsync(e->h_ids.p, e->d_ids.p, tmp_total * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(e->h_cand_offsets.p, e->d_cand_offsets.p, (nc + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(e->h_cand_score.p, e->d_cand_score.p, nc * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(e->h_n_cands.p, e->d_n_cands.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  e->last_d2h = tmp_total * 4 + (nc + 1) * 8 + nc * 4 + n * 4;
+  finish_timing(e);
+  *ids = e->h_ids.p;
+  return SPM_OK;
+}
+
+int spm_sample_encode_ids(spm_engine *e, const char *bytes, const uint64_t *offsets, size_t n, int nbest_size,
+                          float alpha, const int32_t **ids, const uint64_t **id_offsets) {
+  if (!e || !ids || !id_offsets) return SPM_ERR_ARG;
+  if (nbest_size > 512) { e->set_error("nbest_size must be nbest_size <= 512"); return SPM_ERR_ARG; }  // :683
+  if (nbest_size < 0) {
+    e->set_error("SampleEncode with nbest_size < 0 (forward-filtering/backward-sampling) is not on the accelerated path");
+    return SPM_ERR_UNSUPPORTED;
+  }
+  if (nbest_size <= 1) return spm_encode_ids(e, bytes, offsets, n, ids, id_offsets);  // :695-698
+  std::lock_guard<std::mutex> lk(e->mu);
+  auto set_error = [&](const std::string &m) { e->set_error(m); };
+  { const int rc = nbest_args_ok(e, bytes, offsets, n); if (rc) return rc; }
+  CUDA_TRY(cudaSetDevice(e->device));
+  cudaStream_t st = e->stream;
+  const uint32_t K = static_cast<uint32_t>(nbest_size);
+  CUDA_TRY(e->h_id_offsets.ensure(n + 1));
+  CUDA_TRY(e->h_ids.ensure(1));
+  *ids = e->h_ids.p; *id_offsets = e->h_id_offsets.p;
+  e->h_id_offsets.p[0] = 0;
+  if (n == 0) return SPM_OK;
+  e->last_launches = 0;
+  uint64_t tmp_total = 0;
+  { const int rc = e->run_nbest(bytes, offsets, n, K, &tmp_total); if (rc) return rc; }
+  const size_t nc = n * static_cast<size_t>(K);
+  CUDA_TRY(e->h_cand_score.ensure(nc + 1));
+  CUDA_TRY(e->h_n_cands.ensure(n + 1));
+  CUDA_TRY(e->h_picks.ensure(n + 1));
+  CUDA_TRY(cudaMemcpyAsync(e->h_cand_score.p, e->d_cand_score.p, nc * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(e->h_n_cands.p, e->d_n_cands.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  // ---- the draw (sentencepiece_processor.cc:703-718) ----
+  // The uniform of sentence i is generate_canonical<double,53>(mt) exactly as
+  // std::discrete_distribution::operator() takes it; a sentence with fewer than two candidates
+  // draws nothing.  Generated in sentence order on one generator, then the (independent)
+  // log-sum-exp / cumulative tables are evaluated by all host threads.
+  std::vector<double> u(n, 0.0);
+  for (size_t i = 0; i < n; ++i)
+    if (e->h_n_cands.p[i] >= 2) u[i] = std::generate_canonical<double, std::numeric_limits<double>::digits>(e->rng);
+  const float *sc = e->h_cand_score.p;
+  const uint32_t *kc = e->h_n_cands.p;
+  uint32_t *picks = e->h_picks.p;
+  auto work = [&](size_t lo, size_t hi) {
+    std::vector<double> lp(K), cp(K);
+    for (size_t i = lo; i < hi; ++i) {
+      const uint32_t k = kc[i];
+      if (k < 2) { picks[i] = 0; continue; }
+      const float *s = sc + i * K;
+      for (uint32_t c = 0; c < k; ++c) lp[c] = alpha * s[c];  // float product, widened (:705-706)
+      double Z = lp[0];                                       // log_domain::LogSum, util.cc:278-294
+      for (uint32_t c = 1; c < k; ++c) {
+        double xa = Z, xb = lp[c];
+        if (xa > xb) std::swap(xa, xb);
+        Z = xb + std::log1p(std::exp(xa - xb));
+      }
+      double sum = 0.0;
+      for (uint32_t c = 0; c < k; ++c) { lp[c] = std::exp(lp[c] - Z); sum += lp[c]; }
+      double run = 0.0;  // discrete_distribution::param_type::_M_initialize
+      for (uint32_t c = 0; c < k; ++c) { run += lp[c] / sum; cp[c] = run; }
+      cp[k - 1] = 1.0;
+      picks[i] = static_cast<uint32_t>(std::lower_bound(cp.begin(), cp.begin() + k, u[i]) - cp.begin());
+    }
+  };
+  {
+    const size_t T = std::max<size_t>(1, std::min<size_t>(std::thread::hardware_concurrency(), n / 2048 + 1));
+    std::vector<std::thread> th;
+    const size_t per = (n + T - 1) / T;
+    for (size_t t = 1; t < T; ++t) th.emplace_back(work, std::min(n, t * per), std::min(n, (t + 1) * per));
+    work(0, std::min(n, per));
+    for (auto &t : th) t.join();
+  }
+  // ---- gather the picked candidates into sentence order ----
+  CUDA_TRY(e->d_picks.ensure(n));
+  CUDA_TRY(e->d_sent_start.ensure(n));
+  CUDA_TRY(e->d_sent_count.ensure(n));
+  CUDA_TRY(e->d_id_offsets.ensure(n + 1));
+  CUDA_TRY(cudaMemcpyAsync(e->d_picks.p, picks, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  const uint32_t n32 = static_cast<uint32_t>(n);
+  pick_candidates_kernel<<<(n32 + 255) / 256, 256, 0, st>>>(e->d_picks.p, n32, K, e->d_cand_start.p, e->d_cand_count.p,
+                                                           e->d_sent_start.p, e->d_sent_count.p);
+  const uint32_t nb = (n32 + kScanChunk - 1) / kScanChunk;
+  CUDA_TRY(e->d_block_sums.ensure(nb + 1));
+  scan_block_sums_kernel<<<nb, 256, 0, st>>>(e->d_sent_count.p, n32, e->d_block_sums.p, 0);
+  scan_block_prefix_kernel<<<1, 1024, 0, st>>>(e->d_block_sums.p, nb, e->d_ctrl64.p + 2);
+  CUDA_TRY(cudaMemcpyAsync(e->h_ctrl64.p, e->d_ctrl64.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  const unsigned long long tot = e->h_ctrl64.p[2];
+  CUDA_TRY(e->d_ids.ensure(tot + 1));
+  scan_write_gather_kernel<int32_t><<<nb, 256, 0, st>>>(e->d_sent_count.p, n32, e->d_block_sums.p, e->d_id_offsets.p,
+                                                        e->d_sent_start.p, e->d_tmp_ids.p, e->d_ids.p, nullptr, nullptr,
+                                                        e->d_ids.cap, 0, 0ull);
+  CUDA_TRY(cudaGetLastError());
+  e->last_launches += 4;
+  CUDA_TRY(e->h_ids.ensure(tot + 1));
+  if (tot) CUDA_TRY(cudaMemcpyAsync(e->h_ids.p, e->d_ids.p, tot * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(e->h_id_offsets.p, e->d_id_offsets.p, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  e->last_d2h = nc * 4 + n * 4 + tot * 4 + (n + 1) * 8;
+  finish_timing(e);
+  *ids = e->h_ids.p;
+  *id_offsets = e->h_id_offsets.p;
+  return SPM_OK;
 }
 
 int spm_encode_spans(spm_engine *e, const char *bytes, const uint64_t *offsets, size_t n, const int32_t **ids,

@@ -93,6 +93,40 @@ class Engine:
         n2o = np.ctypeslib.as_array(ctypes.cast(p[5], ctypes.POINTER(ctypes.c_uint32)), (tn + n,)).copy()
         return dict(ids=ids, tok_end=te, id_offsets=ido, normalized=norm, norm_offsets=no, n2o=n2o)
 
+    def set_random_seed(self, seed):
+        self._check(self._lib.spm_set_random_seed(self._h, seed))
+
+    def nbest_encode(self, buf, offs, nbest_size):
+        """-> dict(ids, cand_offsets uint64[n*K+1], scores float32[n*K], n_cands uint32[n], K)"""
+        n = len(offs) - 1
+        K = max(1, min(nbest_size, 1024))
+        buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        offs = np.ascontiguousarray(offs, dtype=np.uint64)
+        p = [ctypes.c_void_p() for _ in range(4)]
+        self._check(self._lib.spm_nbest_encode(self._h, buf.ctypes.data, offs.ctypes.data, n, nbest_size,
+                                               *[ctypes.byref(x) for x in p]))
+        nc = n * K
+        co = np.ctypeslib.as_array(ctypes.cast(p[1], ctypes.POINTER(ctypes.c_uint64)), (nc + 1,)).copy()
+        tot = int(co[nc])
+        ids = np.ctypeslib.as_array(ctypes.cast(p[0], ctypes.POINTER(ctypes.c_int32)), (max(tot, 1),))[:tot].copy()
+        sc = np.ctypeslib.as_array(ctypes.cast(p[2], ctypes.POINTER(ctypes.c_float)), (max(nc, 1),))[:nc].copy()
+        nk = np.ctypeslib.as_array(ctypes.cast(p[3], ctypes.POINTER(ctypes.c_uint32)), (max(n, 1),))[:n].copy()
+        return dict(ids=ids, cand_offsets=co, scores=sc, n_cands=nk, K=K)
+
+    def sample_encode(self, buf, offs, nbest_size, alpha):
+        """SampleEncode over a packed batch -> (ids, id_offsets)"""
+        n = len(offs) - 1
+        buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        offs = np.ascontiguousarray(offs, dtype=np.uint64)
+        ids = ctypes.c_void_p()
+        ido = ctypes.c_void_p()
+        self._check(self._lib.spm_sample_encode_ids(self._h, buf.ctypes.data, offs.ctypes.data, n, nbest_size, alpha,
+                                                    ctypes.byref(ids), ctypes.byref(ido)))
+        o = np.ctypeslib.as_array(ctypes.cast(ido, ctypes.POINTER(ctypes.c_uint64)), (n + 1,)).copy()
+        tot = int(o[n])
+        a = np.ctypeslib.as_array(ctypes.cast(ids, ctypes.POINTER(ctypes.c_int32)), (max(tot, 1),))[:tot].copy()
+        return a, o
+
     def encode_device(self, d_bytes_ptr, d_offs_ptr, n, total_bytes, d_ids_ptr, ids_cap, d_id_offs_ptr, stream=None):
         """Device-resident batch (pointers are CUDA device pointers, e.g. torch data_ptr())."""
         tot = ctypes.c_uint64()
