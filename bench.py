@@ -35,6 +35,8 @@ WORKLOADS = {
     "unigram32k_en": ("uni32k", "en", "32k-vocab unigram Viterbi encode, synthetic ~128-byte English sentences"),
     "bpe32k_en": ("bpe32k", "en", "32k-vocab BPE merge encode, synthetic ~128-byte English sentences"),
     "bytefallback_mixed": ("mix_bf8k", "mixed", "byte-fallback unigram + NFKC on mixed CJK/emoji synthetic corpus"),
+    "sample_nbest64_en": ("uni32k", "en", "unigram SampleEncode nbest=64 alpha=0.5 (subword regularization lattice), "
+                          "256k synthetic English sentences"),
 }
 CORPUS_SEED = 20260922
 
@@ -162,6 +164,70 @@ def run_reference_arm(args, rank, world):
     }))
 
 
+def run_sample_workload(args, eng, rank, world, local_rank, mb):
+    """BASELINE.json configs[4]: SampleEncode(nbest_size=64, alpha=0.5) on 256k sentences.  The path goes through
+    the host-buffer C ABI only (n-best on the GPU, the seeded draw on the host), so `value` is the device time of
+    the engine's kernels and `e2e` the wall clock of the synchronous call."""
+    import torch
+    import torch.distributed as dist
+    import corpus
+    n = min(args.sentences, 262144)
+    g = corpus.CorpusGen()
+    buf, offs = g.fill("en", CORPUS_SEED, n, first=rank * n)
+    eng.set_random_seed(12345 + rank)
+    for _ in range(max(1, args.warmup)):
+        eng.sample_encode(buf, offs, 64, 0.5)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    kernel_ms, launches = 0.0, 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ids, ido = eng.sample_encode(buf, offs, 64, 0.5)
+        info = eng.info()
+        kernel_ms += info.last_kernel_ms
+        launches += info.last_kernel_launches
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    clocks = sampler.stop()
+    if world > 1:
+        t = torch.tensor([dt, kernel_ms], device=torch.device("cuda", local_rank))
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt, kernel_ms = float(t[0].item()), float(t[1].item())
+    if rank != 0:
+        return
+    cpu = None
+    if not args.no_cpu:
+        from oracle import oracle_py
+        if oracle_py.ref_available():
+            sample = 20000
+            rm = oracle_py.RefModel(mb)
+            t1 = time.perf_counter()
+            rm.sample_encode_batch(buf, offs[: sample + 1], 64, 0.5, 1)
+            d1 = time.perf_counter() - t1
+            cpu = {"value": sample / d1, "unit": "sentences/s", "cores": 1, "kind": "reference",
+                   "sample": f"first {sample} sentences, one thread over SentencePieceProcessor::SampleEncode (the "
+                             "reference's sampling path is per-call; its thread_local generator makes multi-thread "
+                             "runs non-reproducible)"}
+    total_bytes = int(offs[-1])
+    print(json.dumps({
+        "metric": "sentences_per_sec", "value": world * n * args.steps / (kernel_ms / 1e3), "unit": "sentences/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": kernel_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8 text / int32 ids / f32 lattice scores / f64 sampling", "data": "synthetic",
+        "config": {"workload": args.workload, "model": "uni32k.model", "sentences_per_gpu_per_step": n,
+                   "nbest_size": 64, "alpha": 0.5, "mean_bytes_per_sentence": total_bytes / n,
+                   "value_is": "device time of the engine's kernels (CUDA events)", "e2e_is": "wall clock of "
+                   "spm_sample_encode_ids incl. H2D, n-best kernel, D2H of scores, host draw, gather, D2H of ids"},
+        "clocks": clocks,
+        "e2e": {"value": world * n * args.steps / dt, "unit": "sentences/s", "ms_per_step": dt / args.steps * 1e3,
+                "h2d_bytes_per_step": int(eng.info().last_h2d_bytes), "d2h_bytes_per_step": int(eng.info().last_d2h_bytes)},
+        "gpu_launches": int(launches), "roofline": None, "cpu_baseline": cpu}))
+    eng.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -205,6 +271,9 @@ def main():
     if args.lanes or args.cap or args.threads:
         eng.set_tuning(args.lanes, args.cap, args.threads)
     lib = _capi.load()
+    if args.workload == "sample_nbest64_en":
+        run_sample_workload(args, eng, rank, world, local_rank, mb)
+        return
 
     # ---- this rank's shard, generated straight into pinned host memory ----
     n = args.sentences

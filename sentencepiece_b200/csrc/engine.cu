@@ -885,12 +885,13 @@ int spm_engine::run_nbest(const char *bytes, const uint64_t *offsets, size_t n, 
   NbestGeom G{};
   G.cap = lane_cap;
   G.node_cap = std::min<uint32_t>(65535u, 4 * lane_cap + 64);
-  G.hyp_cap = 16384 + nbest * 96;
+  G.hyp_cap = 6144 + nbest * 64;   // typical need: ~60 hypotheses per result; retried with 8x on overflow
   G.heap_cap = 10000 + 1024 + 512;
-  const int warps_per_cta = 4;
-  const size_t warps_total = static_cast<size_t>(sm_count) * warps_per_cta;
+  int warps_per_cta = 16;
+  size_t warps_total = static_cast<size_t>(sm_count) * warps_per_cta;
   CUDA_TRY(d_lane_slabs.ensure(warps_total * lane_slab_bytes(lane_cap) + 256));
   CUDA_TRY(d_nb_scratch.ensure(warps_total * 32 * nbest_lane_bytes(G) + 256));
+  bool grown = false;
   const size_t nc = n * static_cast<size_t>(nbest);
   CUDA_TRY(d_cand_start.ensure(nc));
   CUDA_TRY(d_cand_count.ensure(nc));
@@ -902,7 +903,7 @@ int spm_engine::run_nbest(const char *bytes, const uint64_t *offsets, size_t n, 
   CUDA_TRY(h_ctrl64.ensure(4));
   // candidates: at most one id per normalized byte each; start from 2 ids per input byte per 8 candidates
   unsigned long long tmp_cap = std::max<unsigned long long>(1u << 20, total_bytes * nbest / 3 + 64ull * n);
-  for (int attempt = 0; attempt < 3; ++attempt) {
+  for (int attempt = 0; attempt < 4; ++attempt) {
     CUDA_TRY(d_tmp_ids.ensure(tmp_cap));
     CUDA_TRY(cudaMemsetAsync(d_ctrl32.p, 0, 16 * sizeof(uint32_t), st));
     CUDA_TRY(cudaMemsetAsync(d_ctrl64.p, 0, 4 * sizeof(unsigned long long), st));
@@ -929,6 +930,16 @@ int spm_engine::run_nbest(const char *bytes, const uint64_t *offsets, size_t n, 
     CUDA_TRY(cudaMemcpyAsync(h_ctrl32.p, d_ctrl32.p, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(h_ctrl64.p, d_ctrl64.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    if (h_ctrl32.p[3] && !grown) {
+      // some sentence needs a larger lattice / hypothesis pool: rerun the batch with roomy slabs on fewer warps
+      grown = true;
+      G.hyp_cap = std::min<uint32_t>(1u << 20, 8 * G.hyp_cap);
+      G.node_cap = 65535u;
+      warps_per_cta = 2;
+      warps_total = static_cast<size_t>(sm_count) * warps_per_cta;
+      CUDA_TRY(d_nb_scratch.ensure(warps_total * 32 * nbest_lane_bytes(G) + 256));
+      continue;
+    }
     if (h_ctrl32.p[3]) {
       set_error("n-best: a sentence exceeds the device path's capacity (normalized length > " + std::to_string(lane_cap) +
                 " bytes, lattice or hypothesis pool too large)");
@@ -1125,6 +1136,8 @@ static void finish_timing(spm_engine *e) {
   float a = 0.f, b = 0.f;
   if (cudaEventElapsedTime(&a, e->ev[0], e->ev[1]) == cudaSuccess) e->last_main_ms = a;
   if (cudaEventElapsedTime(&b, e->ev[0], e->ev[2]) == cudaSuccess) e->last_ms = b;
+  else e->last_ms = e->last_main_ms;
+  (void)cudaGetLastError();  // an unrecorded event must not leave a stale error behind
 }
 
 int spm_encode_ids_device(spm_engine *e, const char *d_bytes, const uint64_t *d_offsets, size_t n, uint64_t total_bytes,
@@ -1294,6 +1307,7 @@ int spm_nbest_encode(spm_engine *e, const char *bytes, const uint64_t *offsets, 
   CUDA_TRY(cudaMemcpyAsync(e->h_cand_offsets.p, e->d_cand_offsets.p, (nc + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaMemcpyAsync(e->h_cand_score.p, e->d_cand_score.p, nc * sizeof(float), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaMemcpyAsync(e->h_n_cands.p, e->d_n_cands.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaEventRecord(e->ev[2], st));
   CUDA_TRY(cudaStreamSynchronize(st));
   e->last_d2h = tmp_total * 4 + (nc + 1) * 8 + nc * 4 + n * 4;
   finish_timing(e);
@@ -1396,6 +1410,7 @@ int spm_sample_encode_ids(spm_engine *e, const char *bytes, const uint64_t *offs
   CUDA_TRY(e->h_ids.ensure(tot + 1));
   if (tot) CUDA_TRY(cudaMemcpyAsync(e->h_ids.p, e->d_ids.p, tot * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaMemcpyAsync(e->h_id_offsets.p, e->d_id_offsets.p, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaEventRecord(e->ev[2], st));
   CUDA_TRY(cudaStreamSynchronize(st));
   e->last_d2h = nc * 4 + n * 4 + tot * 4 + (n + 1) * 8;
   finish_timing(e);

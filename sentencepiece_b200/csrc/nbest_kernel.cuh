@@ -32,7 +32,7 @@ __host__ __device__ inline unsigned long long nbest_lane_bytes(const NbestGeom &
   b += 4ull * (g.cap + 4) * 2;                   // begin_off, end_off u32
   b += g.node_cap * (2ull * 4 + 4ull * 3 + 4);   // npos,nend,nbb,nbe u16; nid,nscore,nbt; end_list u32
   b += g.hyp_cap * (4ull * 3 + 2);               // next u32, fx, gx, node u16
-  b += 4ull * g.heap_cap;
+  b += 8ull * g.heap_cap;                        // agenda entries {fx bits, hypothesis}
   return (b + 15ull) & ~15ull;
 }
 
@@ -47,7 +47,7 @@ struct NbestOut {
   uint32_t *status;                // [1] error, [2] overflow, [3] capacity exceeded (unsupported)
 };
 
-__global__ void __launch_bounds__(128, 1) nbest_lane_kernel(const KModel M, const KBatch B, const NbestOut O,
+__global__ void __launch_bounds__(512, 1) nbest_lane_kernel(const KModel M, const KBatch B, const NbestOut O,
                                                              uint8_t *text_slabs, uint8_t *scratch, const NbestGeom G,
                                                              uint32_t nbest) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(128, 1) nbest_lane_kernel(const KModel M, cons
   uint32_t *hnext = reinterpret_cast<uint32_t *>(sp); sp += 4ull * G.hyp_cap;   // 0xFFFFFFFF = null
   float *hfx = reinterpret_cast<float *>(sp); sp += 4ull * G.hyp_cap;
   float *hgx = reinterpret_cast<float *>(sp); sp += 4ull * G.hyp_cap;
-  uint32_t *heap = reinterpret_cast<uint32_t *>(sp); sp += 4ull * G.heap_cap;
+  uint2 *heap = reinterpret_cast<uint2 *>(sp); sp += 8ull * G.heap_cap;  // {fx bits, hypothesis index}: one load per level
   uint16_t *surf = reinterpret_cast<uint16_t *>(sp); sp += 2ull * (G.cap + 4);
   uint16_t *npos = reinterpret_cast<uint16_t *>(sp); sp += 2ull * G.node_cap;
   uint16_t *nend = reinterpret_cast<uint16_t *>(sp); sp += 2ull * G.node_cap;
@@ -101,30 +101,32 @@ __global__ void __launch_bounds__(128, 1) nbest_lane_kernel(const KModel M, cons
   auto text_byte = [&](uint32_t k) -> uint32_t {
     return (c.text_w[static_cast<size_t>(k >> 2) * 32] >> ((k & 3u) * 8u)) & 0xFFu;
   };
-  // std::push_heap / std::pop_heap on hypothesis indices keyed by fx (comp: a.fx < b.fx)
+  // std::push_heap / std::pop_heap on (fx, hypothesis) entries keyed by fx (comp: a.fx < b.fx)
   auto heap_push = [&](uint32_t &hn, uint32_t v) {
     uint32_t hole = hn++;
     const float fv = hfx[v];
     while (hole > 0) {
       const uint32_t parent = (hole - 1) >> 1;
-      const uint32_t pv = heap[parent];
-      if (!(hfx[pv] < fv)) break;  // equal keys do not move up
-      heap[hole] = pv;
+      const uint2 pe = heap[parent];
+      if (!(__uint_as_float(pe.x) < fv)) break;  // equal keys do not move up
+      heap[hole] = pe;
       hole = parent;
     }
-    heap[hole] = v;
+    heap[hole] = make_uint2(__float_as_uint(fv), v);
   };
   auto heap_pop = [&](uint32_t &hn) -> uint32_t {
-    const uint32_t top = heap[0];
+    const uint32_t top = heap[0].y;
     const uint32_t len = --hn;
     if (len == 0) return top;
-    const uint32_t value = heap[len];
-    const float fv = hfx[value];
+    const uint2 value = heap[len];
+    const float fv = __uint_as_float(value.x);
     uint32_t hole = 0, child = 0;
     while (child < (len - 1) / 2) {  // __adjust_heap
       child = 2 * (child + 1);
-      if (hfx[heap[child]] < hfx[heap[child - 1]]) child--;
-      heap[hole] = heap[child];
+      uint2 ce = heap[child];
+      const uint2 le = heap[child - 1];
+      if (__uint_as_float(ce.x) < __uint_as_float(le.x)) { child--; ce = le; }
+      heap[hole] = ce;
       hole = child;
     }
     if ((len & 1u) == 0 && child == (len - 2) / 2) {
@@ -134,9 +136,9 @@ __global__ void __launch_bounds__(128, 1) nbest_lane_kernel(const KModel M, cons
     }
     while (hole > 0) {  // __push_heap of the saved last element
       const uint32_t parent = (hole - 1) >> 1;
-      const uint32_t pv = heap[parent];
-      if (!(hfx[pv] < fv)) break;
-      heap[hole] = pv;
+      const uint2 pe = heap[parent];
+      if (!(__uint_as_float(pe.x) < fv)) break;
+      heap[hole] = pe;
       hole = parent;
     }
     heap[hole] = value;
@@ -229,9 +231,9 @@ __global__ void __launch_bounds__(128, 1) nbest_lane_kernel(const KModel M, cons
           // fill using a running cursor kept in begin positions of end_list (stable)
           // (second pass: place each node at the next free slot of its end position)
           // use nbt[] as scratch? no: keep a cursor array in the tail of `heap` (unused until A*)
-          for (uint32_t p = 0; p <= L; ++p) heap[p] = end_off[p];
-          end_list[heap[0]++] = 0;
-          for (uint32_t i = 2; i < nn; ++i) end_list[heap[nend[i]]++] = i;
+          for (uint32_t p = 0; p <= L; ++p) heap[p].x = end_off[p];
+          end_list[heap[0].x++] = 0;
+          for (uint32_t i = 2; i < nn; ++i) end_list[heap[nend[i]].x++] = i;
           // ---- Lattice::Viterbi: backtrace scores ----
           for (uint32_t pos = 0; pos <= L; ++pos) {
             const uint32_t rb = pos < L ? begin_off[pos] : 1u, re = pos < L ? begin_off[pos + 1] : 2u;
@@ -311,10 +313,10 @@ __global__ void __launch_bounds__(128, 1) nbest_lane_kernel(const KModel M, cons
             if (hn >= 10000u && !overflow) {  // agenda shrink (:481-505): keep the best `shrink_to`
               // popped in descending order and re-pushed in that order: the heap array becomes that list
               // (stash them in the unused tail of the hypothesis fx array? no -- use the heap's own tail)
-              uint32_t *keep = heap + (G.heap_cap - shrink_to);
-              for (uint32_t i = 0; i < shrink_to; ++i) keep[i] = heap_pop(hn);
+              uint2 *keep = heap + (G.heap_cap - shrink_to);
+              for (uint32_t i = 0; i < shrink_to; ++i) keep[i].y = heap_pop(hn);
               hn = 0;
-              for (uint32_t i = 0; i < shrink_to; ++i) heap_push(hn, keep[i]);
+              for (uint32_t i = 0; i < shrink_to; ++i) heap_push(hn, keep[i].y);
             }
           }
         }
