@@ -110,8 +110,9 @@ __global__ void __launch_bounds__(768, 1) encode_bpe_lane_kernel(const KModel M,
     if (lane == 0) first = atomicAdd(B.work_counter, 32u);
     first = __shfl_sync(0xFFFFFFFFu, first, 0);
     if (first >= B.n) break;
-    const uint32_t sent = first + lane;
-    const bool have = sent < B.n;
+    lane_wait_input(B, first, lane);
+    const bool have = first + lane < B.n;
+    const uint32_t sent = have && B.order ? B.order[first + lane] : first + lane;
     // ---------------- K1 ----------------
     uint32_t n = 0;
     bool defer = false;
@@ -125,6 +126,7 @@ __global__ void __launch_bounds__(768, 1) encode_bpe_lane_kernel(const KModel M,
       }
     }
     __syncwarp();
+    bw = 0xFFFFFFF0u;  // the register window still holds the lane's previous sentence
     // ---------------- K3: word by word ----------------
     uint32_t nlog = 0;  // symbols emitted to the log: id(24) | byte_len << 24
     uint32_t p = 0;     // text position of the next word

@@ -66,6 +66,11 @@ struct KBatch {
   const uint8_t *bytes;
   const uint64_t *offsets;  // [n+1]
   uint32_t n;
+  const uint32_t *order;    // lane kernels: processing order (a permutation of 0..n-1), or null = input order
+  // streamed host batches: *ready = sentences of the whole batch whose bytes have arrived (input order);
+  // this launch covers sentences ready_base .. ready_base + n, which arrive in pieces of 2^piece_shift
+  const uint32_t *ready;
+  uint32_t ready_base, piece_shift;
   // outputs of the encode kernel
   int32_t *tmp_ids;              // ids in completion order
   uint32_t *tmp_tok_end;         // (spans) token end offsets in normalized text, same positions

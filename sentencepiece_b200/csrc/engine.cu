@@ -11,7 +11,9 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cfloat>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -30,6 +32,7 @@
 #include "kernels.cuh"
 #include "lane_kernel.cuh"
 #include "model_reader.h"
+#include "order_kernel.cuh"
 #include "nbest_kernel.cuh"
 #include "trie_builder.h"
 #include "unigram_warp.cuh"
@@ -165,6 +168,26 @@ struct spm_engine {
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
   size_t pipeline_min_sentences = 300000, pipeline_chunk_sentences = 65536;
+  DevBuf<uint32_t> d_order, d_order_hist;  // K0: length-bucketed processing order
+  int build_order(const uint64_t *d_offs, size_t n, cudaStream_t st, const uint32_t **order, uint32_t seg);
+  bool sort_by_length = true;
+  // streamed host batches (encode_host_streamed): set around run_device calls
+  const uint32_t *cur_ready = nullptr;
+  uint32_t cur_ready_base = 0, cur_piece_shift = 0;
+  DevBuf<uint8_t> s_bytes;
+  DevBuf<uint64_t> s_offsets;
+  DevBuf<uint32_t> d_ready;
+  PinBuf<uint32_t> h_marks;
+  cudaEvent_t ev_offs = nullptr;
+  int encode_host_streamed(const char *bytes, const uint64_t *offsets, size_t n, const int32_t **ids,
+                           const uint64_t **id_offsets);
+  // the conditions under which run_device takes a lane kernel for an ids-only batch
+  bool uses_lane_kernel() const {
+    if (G != 1) return false;
+    if (model.model_type == SPM_BPE)
+      return (km.flags & kFlagBpeWordSplit) && (km.flags & kFlagEscapeWs) && !(km.flags & (kFlagHasUserSymbols | kFlagHasUnused));
+    return trie.max_key_len <= 62;
+  }
   // n-best / sampling
   DevBuf<uint8_t> d_nb_scratch;
   DevBuf<unsigned long long> d_cand_start, d_cand_offsets;
@@ -482,13 +505,35 @@ int spm_engine::configure_kernel_attrs() {
   CUDA_TRY(set_smem(encode_unigram_long_kernel<true>, mx));
   CUDA_TRY(set_smem(encode_unigram_lane_kernel, mx));
   CUDA_TRY(set_smem(encode_bpe_lane_kernel, mx));
-  CUDA_TRY(set_smem(nbest_lane_kernel, mx));
+  CUDA_TRY(set_smem(nbest_lane_kernel<kNbestTop, 1024>, mx));
   CUDA_TRY(set_smem(encode_unigram_warp_kernel<512>, mx));
   CUDA_TRY(set_smem(encode_unigram_warp_kernel<1024>, mx));
   CUDA_TRY(set_smem(encode_bpe_kernel<false>, mx));
   CUDA_TRY(set_smem(encode_bpe_kernel<true>, mx));
   CUDA_TRY(set_smem(encode_bpe_long_kernel<false>, mx));
   CUDA_TRY(set_smem(encode_bpe_long_kernel<true>, mx));
+  return SPM_OK;
+}
+
+// K0: sentence indices sorted by byte length, longest first, within segments of `seg` sentences (order_kernel.cuh;
+// seg = 0: the whole batch is one segment); *order = null for tiny batches
+int spm_engine::build_order(const uint64_t *d_offs, size_t n, cudaStream_t st, const uint32_t **order, uint32_t seg) {
+  *order = nullptr;
+  if (!sort_by_length || n <= 64) return SPM_OK;
+  const uint32_t n32 = static_cast<uint32_t>(n);
+  if (seg == 0 || seg > n32) seg = n32;
+  const uint32_t segs = (n32 + seg - 1) / seg;
+  CUDA_TRY(d_order.ensure(n));
+  CUDA_TRY(d_order_hist.ensure(static_cast<size_t>(segs) * kOrderBuckets));
+  CUDA_TRY(cudaMemsetAsync(d_order_hist.p, 0, static_cast<size_t>(segs) * kOrderBuckets * sizeof(uint32_t), st));
+  const uint32_t per_block = kOrderThreads * kOrderPerThread;
+  const dim3 grid((seg + per_block - 1) / per_block, segs);
+  order_hist_kernel<<<grid, kOrderThreads, 0, st>>>(d_offs, n32, seg, d_order_hist.p);
+  order_scan_kernel<<<segs, kOrderBuckets, 0, st>>>(d_order_hist.p);
+  order_scatter_kernel<<<grid, kOrderThreads, 0, st>>>(d_offs, n32, seg, d_order_hist.p, d_order.p);
+  CUDA_TRY(cudaGetLastError());
+  last_launches += 3;
+  *order = d_order.p;
   return SPM_OK;
 }
 
@@ -596,6 +641,13 @@ int spm_engine::run_device(const uint8_t *d_bytes_base, const uint64_t *d_offs, 
     B.tile_bytes = geom.tile_bytes;
 
     CUDA_TRY(cudaEventRecord(ev[0], st));
+    if (lane_path || bpe_lane_path) {
+      const int rc = build_order(d_offs, n, st, &B.order, cur_ready ? (1u << cur_piece_shift) : 0u);
+      if (rc) return rc;
+      B.ready = cur_ready;
+      B.ready_base = cur_ready_base;
+      B.piece_shift = cur_piece_shift;
+    }
     if (bpe_lane_path) {
       encode_bpe_lane_kernel<<<grid, bpe_lane_threads, geom.smem_bytes, st>>>(M, B, d_lane_slabs.p, lane_cap);
     } else if (bpe) {
@@ -714,7 +766,8 @@ int spm_engine::run_device(const uint8_t *d_bytes_base, const uint64_t *d_offs, 
       h_ctrl32.p[2] |= h_ctrl32.p[10];
     }
     if (h_ctrl32.p[1]) {
-      set_error("encode failed: internal consistency check (status " + std::to_string(h_ctrl32.p[1]) + ")");
+      if (h_ctrl32.p[1] & 2u) set_error("encode failed: the host-to-device copy of a streamed batch made no progress for 3 s");
+      else set_error("encode failed: internal consistency check (status " + std::to_string(h_ctrl32.p[1]) + ")");
       return SPM_ERR_ENCODE;
     }
     if (h_ctrl32.p[2]) {  // temporary buffers too small: cursors hold the exact requirement
@@ -801,7 +854,12 @@ int spm_engine::encode_host_pipelined(const char *bytes, const uint64_t *offsets
   // kernels against 6.5 ms for one launch)
   const bool is_bpe = model.model_type == SPM_BPE;
   const size_t warps = static_cast<size_t>(sm_count) * ctas_per_sm * ((is_bpe ? std::min(threads, 768) : threads) / 32);
-  const size_t chunk = std::max<size_t>(pipeline_chunk_sentences, warps * 32 * (is_bpe ? 2 : 1));
+  size_t groups_per_warp = is_bpe ? 2 : 1;
+  if (const char *v = getenv("SPM_B200_CHUNK_GROUPS")) groups_per_warp = std::max(1, atoi(v));
+  const bool trace = getenv("SPM_B200_TRACE") != nullptr;
+  const auto t_begin = std::chrono::steady_clock::now();
+  auto now_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
+  const size_t chunk = std::max<size_t>(pipeline_chunk_sentences, warps * 32 * groups_per_warp);
   const size_t C = (n + chunk - 1) / chunk;
   const uint64_t total_bytes = offsets[n] - offsets[0];
   CUDA_TRY(h_id_offsets.ensure(n + 1));
@@ -829,6 +887,7 @@ int spm_engine::encode_host_pipelined(const char *bytes, const uint64_t *offsets
   uint64_t launches = 0, deferred = 0;
   float main_ms = 0.f, all_ms = 0.f;
   unsigned long long id_base = 0;
+  if (trace) fprintf(stderr, "[trace] setup done at %.3f ms\n", now_ms());
   { const int rc = issue_h2d(0); if (rc) return rc; }
   for (size_t c = 0; c < C; ++c) {
     const int k = static_cast<int>(c & 1);
@@ -840,6 +899,7 @@ int spm_engine::encode_host_pipelined(const char *bytes, const uint64_t *offsets
     const int rc = run_device(p_bytes[k].p - offsets[lo], p_offsets[k].p, hi - lo, offsets[hi] - offsets[lo], false, nullptr, 0,
                               nullptr, &tot, nullptr, stream, &p_ids[k], &p_id_offsets[k], id_base);
     if (rc) { cudaDeviceSynchronize(); return rc; }
+    const double t_ret = trace ? now_ms() : 0.0;
     CUDA_TRY(cudaEventRecord(ev_out[k], stream));
     launches += last_launches;
     deferred += last_deferred;
@@ -858,14 +918,147 @@ int spm_engine::encode_host_pipelined(const char *bytes, const uint64_t *offsets
     CUDA_TRY(cudaEventRecord(ev_d2h[k], s_d2h));
     float a = 0.f;
     if (cudaEventElapsedTime(&a, ev[0], ev[1]) == cudaSuccess) { main_ms += a; all_ms += a; }
+    if (trace) fprintf(stderr, "[trace] chunk %zu: run_device returned at %.3f ms (encode kernel %.3f ms), D2H issued at %.3f ms\n", c,
+                       t_ret, a, now_ms());
     id_base += tot;
   }
+  if (trace) fprintf(stderr, "[trace] all chunks issued at %.3f ms\n", now_ms());
   CUDA_TRY(cudaStreamSynchronize(s_d2h));
+  if (trace) fprintf(stderr, "[trace] results on host at %.3f ms (%zu chunks of %zu)\n", now_ms(), C, chunk);
   last_launches = launches;
   last_deferred = deferred;
   last_main_ms = main_ms;
   last_ms = all_ms;
   last_h2d = total_bytes + (n + C) * sizeof(uint64_t);
+  last_d2h = id_base * sizeof(int32_t) + (n + C) * sizeof(uint64_t);
+  *ids = h_ids.p;
+  *id_offsets = h_id_offsets.p;
+  return SPM_OK;
+}
+
+// Large host batches through the lane kernels: streamed input.  Every H2D copy of the batch is queued up front in
+// pieces of 32k sentences, each followed by a 4-byte copy that advances a device-side watermark; the encode kernels
+// cover a few large chunks (>= 2 sentence groups per resident warp, so that the length-ordered dynamic schedule can
+// balance them) and their warps wait on the watermark for the piece that holds their group.  The kernel of a chunk
+// therefore starts as soon as its first piece has landed instead of after the whole chunk, and the D2H of chunk c
+// overlaps the encode of chunk c + 1.
+int spm_engine::encode_host_streamed(const char *bytes, const uint64_t *offsets, size_t n, const int32_t **ids,
+                                     const uint64_t **id_offsets) {
+  CUDA_TRY(cudaSetDevice(device));
+  if (!s_h2d) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&s_h2d, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&s_d2h, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; ++k) {
+      CUDA_TRY(cudaEventCreateWithFlags(&ev_in[k], cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&ev_out[k], cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&ev_d2h[k], cudaEventDisableTiming));
+    }
+  }
+  if (!ev_offs) CUDA_TRY(cudaEventCreateWithFlags(&ev_offs, cudaEventDisableTiming));
+  const bool trace = getenv("SPM_B200_TRACE") != nullptr;
+  const auto t_begin = std::chrono::steady_clock::now();
+  auto now_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
+  constexpr uint32_t kPieceShift = 15;
+  constexpr size_t kPiece = size_t{1} << kPieceShift;
+  const size_t P = (n + kPiece - 1) / kPiece;
+  const bool is_bpe = model.model_type == SPM_BPE;
+  const size_t warps = static_cast<size_t>(sm_count) * ctas_per_sm * ((is_bpe ? std::min(threads, 768) : threads) / 32);
+  size_t groups_per_warp = is_bpe ? 4 : 2;
+  if (const char *v = getenv("SPM_B200_CHUNK_GROUPS")) groups_per_warp = std::max(1, atoi(v));
+  const size_t min_chunk = std::max<size_t>(kPiece, warps * 32 * groups_per_warp);
+  const size_t want_chunks = std::max<size_t>(1, n / min_chunk);
+  const size_t chunk = ((P + want_chunks - 1) / want_chunks) * kPiece;
+  const size_t C = (n + chunk - 1) / chunk;
+  const uint64_t total_bytes = offsets[n] - offsets[0];
+  CUDA_TRY(s_bytes.ensure(total_bytes + 64));
+  CUDA_TRY(s_offsets.ensure(n + 1));
+  CUDA_TRY(d_ready.ensure(4));
+  CUDA_TRY(h_marks.ensure(P + 1));
+  CUDA_TRY(h_id_offsets.ensure(n + 1));
+  CUDA_TRY(h_ids.ensure(std::max<size_t>(h_ids.cap, total_bytes / 3 + 2 * n + 4096)));
+  // ---- queue the whole input ----
+  CUDA_TRY(cudaMemsetAsync(d_ready.p, 0, sizeof(uint32_t), s_h2d));
+  CUDA_TRY(cudaMemcpyAsync(s_offsets.p, offsets, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s_h2d));
+  CUDA_TRY(cudaEventRecord(ev_offs, s_h2d));
+  {
+    uint64_t bad = 0;  // checked while the offsets are on their way
+    for (size_t i = 0; i < n; ++i) bad |= static_cast<uint64_t>(offsets[i + 1] < offsets[i]);
+    if (bad) {
+      cudaStreamSynchronize(s_h2d);
+      set_error("offsets must be non-decreasing");
+      return SPM_ERR_ARG;
+    }
+  }
+  // The copies are issued by a helper thread so that the first encode kernel is launched right away.  Cuts between
+  // the copies sit on 128-byte lines of the device buffer (ByteStream in lane_kernel.cuh over-reads within a line).
+  std::atomic<int> feed_rc{0};
+  std::thread feeder([&]() {
+    if (cudaSetDevice(device) != cudaSuccess) { feed_rc = 1; return; }
+    uint64_t done_bytes = 0;
+    for (size_t p = 0; p < P; ++p) {
+      const size_t hi = std::min(n, (p + 1) * kPiece);
+      uint64_t cut = offsets[hi] - offsets[0];
+      cut = hi == n ? total_bytes : std::min<uint64_t>(total_bytes, (cut + 127u) & ~uint64_t{127});
+      if (cut > done_bytes &&
+          cudaMemcpyAsync(s_bytes.p + done_bytes, bytes + offsets[0] + done_bytes, cut - done_bytes, cudaMemcpyHostToDevice,
+                          s_h2d) != cudaSuccess) { feed_rc = 1; return; }
+      done_bytes = std::max(done_bytes, cut);
+      h_marks.p[p] = static_cast<uint32_t>(hi);
+      if (cudaMemcpyAsync(d_ready.p, h_marks.p + p, sizeof(uint32_t), cudaMemcpyHostToDevice, s_h2d) != cudaSuccess) {
+        feed_rc = 1;
+        return;
+      }
+    }
+  });
+  struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{feeder};
+  CUDA_TRY(cudaStreamWaitEvent(stream, ev_offs, 0));
+  uint64_t launches = 0, deferred = 0;
+  float main_ms = 0.f, all_ms = 0.f;
+  unsigned long long id_base = 0;
+  for (size_t c = 0; c < C; ++c) {
+    const int k = static_cast<int>(c & 1);
+    const size_t lo = c * chunk, hi = std::min(n, lo + chunk);
+    if (c >= 2) CUDA_TRY(cudaStreamWaitEvent(stream, ev_d2h[k], 0));  // the slot's previous results have left the GPU
+    uint64_t tot = 0;
+    cur_ready = d_ready.p;
+    cur_ready_base = static_cast<uint32_t>(lo);
+    cur_piece_shift = kPieceShift;
+    const int rc = run_device(s_bytes.p - offsets[0], s_offsets.p + lo, hi - lo, offsets[hi] - offsets[lo], false, nullptr, 0,
+                              nullptr, &tot, nullptr, stream, &p_ids[k], &p_id_offsets[k], id_base);
+    cur_ready = nullptr;
+    if (rc) { cudaDeviceSynchronize(); return rc; }
+    const double t_ret = trace ? now_ms() : 0.0;
+    CUDA_TRY(cudaEventRecord(ev_out[k], stream));
+    launches += last_launches;
+    deferred += last_deferred;
+    if (id_base + tot + 1 > h_ids.cap) {  // grow the pinned result buffer (rare): keep what has already arrived
+      CUDA_TRY(cudaStreamSynchronize(s_d2h));
+      PinBuf<int32_t> bigger;
+      const double per_sent = static_cast<double>(id_base + tot) / static_cast<double>(hi);
+      CUDA_TRY(bigger.ensure(static_cast<size_t>(per_sent * 1.25 * n) + tot + 4096));
+      if (id_base) memcpy(bigger.p, h_ids.p, id_base * sizeof(int32_t));
+      h_ids.release();
+      h_ids = bigger;
+    }
+    CUDA_TRY(cudaStreamWaitEvent(s_d2h, ev_out[k], 0));
+    if (tot) CUDA_TRY(cudaMemcpyAsync(h_ids.p + id_base, p_ids[k].p, tot * sizeof(int32_t), cudaMemcpyDeviceToHost, s_d2h));
+    CUDA_TRY(cudaMemcpyAsync(h_id_offsets.p + lo, p_id_offsets[k].p, (hi - lo + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, s_d2h));
+    CUDA_TRY(cudaEventRecord(ev_d2h[k], s_d2h));
+    float a = 0.f;
+    if (cudaEventElapsedTime(&a, ev[0], ev[1]) == cudaSuccess) { main_ms += a; all_ms += a; }
+    if (trace) fprintf(stderr, "[trace] chunk %zu (%zu sentences): run_device returned at %.3f ms (encode kernel %.3f ms)\n", c,
+                       hi - lo, t_ret, a);
+    id_base += tot;
+  }
+  feeder.join();
+  if (feed_rc) { cudaDeviceSynchronize(); set_error("host-to-device copy of a streamed batch failed"); return SPM_ERR_CUDA; }
+  CUDA_TRY(cudaStreamSynchronize(s_d2h));
+  if (trace) fprintf(stderr, "[trace] results on host at %.3f ms\n", now_ms());
+  last_launches = launches;
+  last_deferred = deferred;
+  last_main_ms = main_ms;
+  last_ms = all_ms;
+  last_h2d = total_bytes + (n + 1) * sizeof(uint64_t) + P * sizeof(uint32_t);
   last_d2h = id_base * sizeof(int32_t) + (n + C) * sizeof(uint64_t);
   *ids = h_ids.p;
   *id_offsets = h_id_offsets.p;
@@ -886,9 +1079,13 @@ int spm_engine::run_nbest(const char *bytes, const uint64_t *offsets, size_t n, 
   G.cap = lane_cap;
   G.node_cap = std::min<uint32_t>(65535u, 4 * lane_cap + 64);
   G.hyp_cap = 6144 + nbest * 64;   // typical need: ~60 hypotheses per result; retried with 8x on overflow
-  G.heap_cap = 10000 + 1024 + 512;
-  int warps_per_cta = 16;
-  size_t warps_total = static_cast<size_t>(sm_count) * warps_per_cta;
+  G.heap_cap = 10000 + 1024 + 512;  // even: keeps the child pairs of the agenda 16-byte aligned
+  // 32 warps per SM (64 registers per lane): the search is bound by L2 / HBM transactions on the per-lane agendas, and
+  // measured throughput still rises from 16 to 32 warps (188 -> 157 ms for 256k sentences, nbest 64)
+  const size_t groups = std::max<size_t>(1, (n + 31) / 32);   // one group of 32 sentences per warp pass
+  int ctas = static_cast<int>(std::min<size_t>(sm_count, groups));
+  int warps_per_cta = static_cast<int>(std::min<size_t>(32, (groups + ctas - 1) / ctas));
+  size_t warps_total = static_cast<size_t>(ctas) * warps_per_cta;
   CUDA_TRY(d_lane_slabs.ensure(warps_total * lane_slab_bytes(lane_cap) + 256));
   CUDA_TRY(d_nb_scratch.ensure(warps_total * 32 * nbest_lane_bytes(G) + 256));
   bool grown = false;
@@ -923,7 +1120,9 @@ int spm_engine::run_nbest(const char *bytes, const uint64_t *offsets, size_t n, 
     O.n_cands = d_n_cands.p;
     O.status = d_ctrl32.p;
     CUDA_TRY(cudaEventRecord(ev[0], st));
-    nbest_lane_kernel<<<sm_count, warps_per_cta * 32, kLaneTableBytes, st>>>(km, B, O, d_lane_slabs.p, d_nb_scratch.p, G, nbest);
+    { const int rc = build_order(d_offsets.p, n, st, &B.order, 0); if (rc) return rc; }
+    nbest_lane_kernel<kNbestTop, 1024><<<ctas, warps_per_cta * 32, nbest_smem_bytes<kNbestTop>(warps_per_cta), st>>>(
+        km, B, O, d_lane_slabs.p, d_nb_scratch.p, G, nbest);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(ev[1], st));
     ++last_launches;
@@ -936,7 +1135,8 @@ int spm_engine::run_nbest(const char *bytes, const uint64_t *offsets, size_t n, 
       G.hyp_cap = std::min<uint32_t>(1u << 20, 8 * G.hyp_cap);
       G.node_cap = 65535u;
       warps_per_cta = 2;
-      warps_total = static_cast<size_t>(sm_count) * warps_per_cta;
+      ctas = sm_count;
+      warps_total = static_cast<size_t>(ctas) * warps_per_cta;
       CUDA_TRY(d_nb_scratch.ensure(warps_total * 32 * nbest_lane_bytes(G) + 256));
       continue;
     }
@@ -980,6 +1180,7 @@ static int create_common(spm_engine *e, int device, spm_engine **out) {
   if (prop.major < 10) return fail(SPM_ERR_CUDA, "this build targets sm_100a (B200); found compute capability " +
                                                       std::to_string(prop.major) + "." + std::to_string(prop.minor));
   e->sm_count = prop.multiProcessorCount;
+  if (const char *v = getenv("SPM_B200_SORT")) e->sort_by_length = atoi(v) != 0;  // A/B knob for profiles/
   e->smem_optin = prop.sharedMemPerBlockOptin;
   if (cudaSetDevice(device) != cudaSuccess) return fail(SPM_ERR_CUDA, "cudaSetDevice failed");
   int rc = e->build_tables();
@@ -1056,6 +1257,9 @@ void spm_engine_destroy(spm_engine *e) {
     if (e->ev_out[k]) cudaEventDestroy(e->ev_out[k]);
     if (e->ev_d2h[k]) cudaEventDestroy(e->ev_d2h[k]);
   }
+  e->s_bytes.release(); e->s_offsets.release(); e->d_ready.release(); e->h_marks.release();
+  e->d_order.release(); e->d_order_hist.release();
+  if (e->ev_offs) cudaEventDestroy(e->ev_offs);
   if (e->s_h2d) cudaStreamDestroy(e->s_h2d);
   if (e->s_d2h) cudaStreamDestroy(e->s_d2h);
   e->h_ids.release(); e->h_tok_end.release(); e->h_n2o.release(); e->h_ctrl32.release(); e->h_deferred.release();
@@ -1233,6 +1437,7 @@ int spm_encode_ids(spm_engine *e, const char *bytes, const uint64_t *offsets, si
                    const uint64_t **id_offsets) {
   if (e && offsets && ids && id_offsets && bytes && n >= e->pipeline_min_sentences && n < 0xFFFFFFF0ull) {
     std::lock_guard<std::mutex> lk(e->mu);
+    if (e->uses_lane_kernel()) return e->encode_host_streamed(bytes, offsets, n, ids, id_offsets);
     return e->encode_host_pipelined(bytes, offsets, n, ids, id_offsets);
   }
   return encode_host(e, bytes, offsets, n, false, ids, nullptr, id_offsets, nullptr, nullptr, nullptr);

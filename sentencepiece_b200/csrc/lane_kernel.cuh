@@ -41,6 +41,31 @@ __host__ __device__ inline unsigned long long lane_slab_bytes(uint32_t cap) {
 // shared memory for the normalizer's fast-path tables
 constexpr uint32_t kLaneTableBytes = 32 + 4096 + 512 + 16;  // cm_lead[8] + cm_pair[1024] + cm_solo[128] + plain[4]
 
+// Streamed host batches (engine.cu, encode_host_streamed): the batch arrives in pieces of 2^piece_shift
+// sentences and *B.ready counts the sentences whose bytes are in HBM.  Lane 0 of a warp waits for the piece
+// that holds its group; the wait is bounded so that a stalled copy can never hang the GPU.
+__device__ __forceinline__ void lane_wait_input(const KBatch &B, uint32_t first, uint32_t lane) {
+  if (!B.ready) return;
+  if (lane == 0) {
+    uint32_t need = ((first >> B.piece_shift) + 1u) << B.piece_shift;
+    if (need > B.n) need = B.n;
+    need += B.ready_base;
+    const volatile uint32_t *r = B.ready;
+    if (*r < need) {
+      const long long t0 = clock64();
+      while (*r < need) {
+        __nanosleep(200);
+        if (clock64() - t0 > 6000000000ll || (*reinterpret_cast<const volatile uint32_t *>(B.status + 1) & 2u)) {
+          atomicOr(B.status + 1, 2u);  // ~3 s without progress: give up (the host reports the error)
+          break;
+        }
+      }
+    }
+    __threadfence();
+  }
+  __syncwarp();
+}
+
 struct LaneCtx {
   uint32_t *text_w;  // + word*32 (already offset by lane)
   uint32_t *log;     // + t*32    (already offset by lane)
@@ -52,7 +77,10 @@ struct LaneCtx {
 };
 
 // Sequential byte stream over a lane's input: 16-byte aligned chunks (next chunk prefetched)
-// feed a 64-bit shift register that always exposes the next >= 4 bytes.
+// feed a 64-bit shift register that always exposes the next >= 4 bytes.  The aligned chunks
+// over-read into the neighbouring sentences by up to 15 bytes; a streamed host batch (engine.cu)
+// therefore cuts its copies at 128-byte lines, so that every line a sentence touches has landed
+// completely before the sentence's piece is announced.
 struct ByteStream {
   const uint4 *cp;      // chunk that `nxt` was loaded from, + 1
   const uint4 *cend;    // first chunk past the sentence
@@ -224,8 +252,9 @@ __device__ __forceinline__ uint32_t lane_normalize(const KModel &M, const uint8_
       }
     }
     // ---- generic path: rule targets and verbatim user symbols ----
+    auto sp_byte = [&](uint32_t i) -> uint32_t { return __ldg(sp + i); };
     if (!started) {
-      if (spl == 1 && __ldg(sp) == ' ') {  // a chunk that is exactly " " during the heading loop
+      if (spl == 1 && sp_byte(0) == ' ') {  // a chunk that is exactly " " during the heading loop
         pos += consumed;
         if (consumed <= 4) S.consume(consumed); else S.init(in + pos, in + len);
         continue;
@@ -235,11 +264,11 @@ __device__ __forceinline__ uint32_t lane_normalize(const KModel &M, const uint8_
     }
     {
       uint32_t i0 = 0;
-      while (is_prev_space && i0 < spl && __ldg(sp + i0) == ' ') ++i0;  // :137-138
+      while (is_prev_space && i0 < spl && sp_byte(i0) == ' ') ++i0;  // :137-138
       if (i0 < spl) {
         uint32_t last = 0;
         for (uint32_t i = i0; i < spl; ++i) {
-          last = __ldg(sp + i);
+          last = sp_byte(i);
           if (last == ' ' && esc) { put(0xE2); put(0x96); put(0x81); } else put(last);
         }
         is_prev_space = last == ' ';
@@ -317,8 +346,9 @@ __global__ void __launch_bounds__(1024, 1) encode_unigram_lane_kernel(const KMod
     if (lane == 0) first = atomicAdd(B.work_counter, 32u);
     first = __shfl_sync(0xFFFFFFFFu, first, 0);
     if (first >= B.n) break;
-    const uint32_t sent = first + lane;
-    const bool have = sent < B.n;
+    lane_wait_input(B, first, lane);
+    const bool have = first + lane < B.n;
+    const uint32_t sent = have && B.order ? B.order[first + lane] : first + lane;
     // ---------------- K1 ----------------
     uint32_t n = 0;
     bool defer = false;

@@ -22,18 +22,32 @@ namespace spm_b200 {
 
 struct NbestGeom {
   uint32_t cap;        // normalized bytes per sentence
-  uint32_t node_cap;   // lattice nodes per sentence
+  uint32_t node_cap;   // lattice nodes per sentence (<= 65535: hypotheses hold 16-bit node indices)
   uint32_t hyp_cap;    // hypotheses per sentence
-  uint32_t heap_cap;   // agenda entries (>= 10000 + fan-out)
+  uint32_t heap_cap;   // agenda entries (>= 10000 + fan-out + 512 for the shrink list)
 };
+// per-lane scratch in HBM, 16-byte records so that one load / store moves a whole hypothesis or node:
+//   hyp  [hyp_cap]     uint4 {next, gx bits, node | ids_so_far << 16, begin char | unk << 16}
+//   heap [heap_cap+2]  uint2 {fx bits, hypothesis}; entry i lives in slot i + 1, which puts the children
+//                      (2k+1, 2k+2) of any entry in one aligned 16-byte pair (one load per level of a pop)
+//   node [node_cap]    uint4 {id, score bits, backtrace bits, begin char | end char << 16}   creation order
+//   elist[node_cap]    uint4 {node | begin char << 16, backtrace bits, score bits, ids | unk << 31}   sorted by end char
+//   end_off[cap+4] u32, maxbt[cap+4] f32 (reused as the sort cursors), surf[cap+4] u16
 __host__ __device__ inline unsigned long long nbest_lane_bytes(const NbestGeom &g) {
   unsigned long long b = 0;
-  b += 2ull * (g.cap + 4);                       // surf u16
-  b += 4ull * (g.cap + 4) * 2;                   // begin_off, end_off u32
-  b += g.node_cap * (2ull * 4 + 4ull * 3 + 4);   // npos,nend,nbb,nbe u16; nid,nscore,nbt; end_list u32
-  b += g.hyp_cap * (4ull * 3 + 2);               // next u32, fx, gx, node u16
-  b += 8ull * g.heap_cap;                        // agenda entries {fx bits, hypothesis}
+  b += 16ull * g.hyp_cap;
+  b += 8ull * (g.heap_cap + 2);
+  b += 32ull * g.node_cap;
+  b += 4ull * (g.cap + 4) * 2;
+  b += 2ull * (g.cap + 4);
   return (b + 15ull) & ~15ull;
+}
+// agenda entries kept in shared memory per lane (the top levels of the binary heap); odd, so that a pair of
+// children never straddles the shared / global boundary
+constexpr int kNbestTop = 15;
+template <int TOP>
+__host__ __device__ constexpr uint32_t nbest_smem_bytes(uint32_t warps) {
+  return kLaneTableBytes + warps * 32u * 8u * TOP;
 }
 
 struct NbestOut {
@@ -47,9 +61,10 @@ struct NbestOut {
   uint32_t *status;                // [1] error, [2] overflow, [3] capacity exceeded (unsupported)
 };
 
-__global__ void __launch_bounds__(512, 1) nbest_lane_kernel(const KModel M, const KBatch B, const NbestOut O,
-                                                             uint8_t *text_slabs, uint8_t *scratch, const NbestGeom G,
-                                                             uint32_t nbest) {
+template <int TOP, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) nbest_lane_kernel(const KModel M, const KBatch B, const NbestOut O,
+                                                                 uint8_t *text_slabs, uint8_t *scratch, const NbestGeom G,
+                                                                 uint32_t nbest) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint32_t *s_tab = reinterpret_cast<uint32_t *>(smem);
   for (uint32_t i = threadIdx.x; i < kLaneTableBytes / 4; i += blockDim.x) {
@@ -76,24 +91,18 @@ __global__ void __launch_bounds__(512, 1) nbest_lane_kernel(const KModel M, cons
     c.s_solo = reinterpret_cast<const int32_t *>(s_tab + 8 + 1024);
     c.s_plain = s_tab + 8 + 1024 + 128;
   }
+  // agenda top: [warp][entry][lane]
+  uint2 *s_top = reinterpret_cast<uint2 *>(smem + kLaneTableBytes) + static_cast<size_t>(threadIdx.x >> 5) * (32 * TOP) + lane;
   // per-lane scratch
   uint8_t *sp = scratch + (static_cast<size_t>(warp_global) * 32 + lane) * nbest_lane_bytes(G);
-  uint32_t *begin_off = reinterpret_cast<uint32_t *>(sp); sp += 4ull * (G.cap + 4);
+  uint4 *hyp = reinterpret_cast<uint4 *>(sp); sp += 16ull * G.hyp_cap;
+  uint2 *heap = reinterpret_cast<uint2 *>(sp); sp += 8ull * (G.heap_cap + 2);   // slot = entry + 1
+  uint4 *node = reinterpret_cast<uint4 *>(sp); sp += 16ull * G.node_cap;
+  uint4 *elist = reinterpret_cast<uint4 *>(sp); sp += 16ull * G.node_cap;
   uint32_t *end_off = reinterpret_cast<uint32_t *>(sp); sp += 4ull * (G.cap + 4);
-  int32_t *nid = reinterpret_cast<int32_t *>(sp); sp += 4ull * G.node_cap;
-  float *nscore = reinterpret_cast<float *>(sp); sp += 4ull * G.node_cap;
-  float *nbt = reinterpret_cast<float *>(sp); sp += 4ull * G.node_cap;
-  uint32_t *end_list = reinterpret_cast<uint32_t *>(sp); sp += 4ull * G.node_cap;
-  uint32_t *hnext = reinterpret_cast<uint32_t *>(sp); sp += 4ull * G.hyp_cap;   // 0xFFFFFFFF = null
-  float *hfx = reinterpret_cast<float *>(sp); sp += 4ull * G.hyp_cap;
-  float *hgx = reinterpret_cast<float *>(sp); sp += 4ull * G.hyp_cap;
-  uint2 *heap = reinterpret_cast<uint2 *>(sp); sp += 8ull * G.heap_cap;  // {fx bits, hypothesis index}: one load per level
-  uint16_t *surf = reinterpret_cast<uint16_t *>(sp); sp += 2ull * (G.cap + 4);
-  uint16_t *npos = reinterpret_cast<uint16_t *>(sp); sp += 2ull * G.node_cap;
-  uint16_t *nend = reinterpret_cast<uint16_t *>(sp); sp += 2ull * G.node_cap;
-  uint16_t *nbb = reinterpret_cast<uint16_t *>(sp); sp += 2ull * G.node_cap;
-  uint16_t *nbe = reinterpret_cast<uint16_t *>(sp); sp += 2ull * G.node_cap;
-  uint16_t *hnode = reinterpret_cast<uint16_t *>(sp);
+  float *maxbt = reinterpret_cast<float *>(sp); sp += 4ull * (G.cap + 4);
+  uint16_t *surf = reinterpret_cast<uint16_t *>(sp);
+  uint32_t *sort_cur = reinterpret_cast<uint32_t *>(maxbt);  // maxbt is dead once the nodes exist
 
   const uint2 *node2 = M.trie_node2;
   const uint32_t root = __ldg(&node2[0]).x;
@@ -101,47 +110,59 @@ __global__ void __launch_bounds__(512, 1) nbest_lane_kernel(const KModel M, cons
   auto text_byte = [&](uint32_t k) -> uint32_t {
     return (c.text_w[static_cast<size_t>(k >> 2) * 32] >> ((k & 3u) * 8u)) & 0xFFu;
   };
-  // std::push_heap / std::pop_heap on (fx, hypothesis) entries keyed by fx (comp: a.fx < b.fx)
-  auto heap_push = [&](uint32_t &hn, uint32_t v) {
+  auto hget = [&](uint32_t i) -> uint2 { return i < TOP ? s_top[i * 32] : heap[i + 1]; };
+  auto hset = [&](uint32_t i, uint2 e) {
+    if (i < TOP) s_top[i * 32] = e;
+    else heap[i + 1] = e;
+  };
+  // std::push_heap / std::pop_heap on {fx, hypothesis} entries keyed by fx (comp: a.fx < b.fx)
+  auto heap_push = [&](uint32_t &hn, uint2 e) {
     uint32_t hole = hn++;
-    const float fv = hfx[v];
+    const float fv = __uint_as_float(e.x);
     while (hole > 0) {
       const uint32_t parent = (hole - 1) >> 1;
-      const uint2 pe = heap[parent];
+      const uint2 pe = hget(parent);
       if (!(__uint_as_float(pe.x) < fv)) break;  // equal keys do not move up
-      heap[hole] = pe;
+      hset(hole, pe);
       hole = parent;
     }
-    heap[hole] = make_uint2(__float_as_uint(fv), v);
+    hset(hole, e);
   };
-  auto heap_pop = [&](uint32_t &hn) -> uint32_t {
-    const uint32_t top = heap[0].y;
+  auto heap_pop = [&](uint32_t &hn) -> uint2 {
+    const uint2 top = hget(0);
     const uint32_t len = --hn;
     if (len == 0) return top;
-    const uint2 value = heap[len];
+    const uint2 value = hget(len);
     const float fv = __uint_as_float(value.x);
     uint32_t hole = 0, child = 0;
-    while (child < (len - 1) / 2) {  // __adjust_heap
+    while (child < (len - 1) / 2) {  // __adjust_heap: move the larger child up (the right one on ties)
       child = 2 * (child + 1);
-      uint2 ce = heap[child];
-      const uint2 le = heap[child - 1];
-      if (__uint_as_float(ce.x) < __uint_as_float(le.x)) { child--; ce = le; }
-      heap[hole] = ce;
+      uint2 le, re;
+      if (child < TOP) {
+        re = s_top[child * 32];
+        le = s_top[(child - 1) * 32];
+      } else {
+        const uint4 pr = *reinterpret_cast<const uint4 *>(heap + child);  // slots child, child + 1
+        le = make_uint2(pr.x, pr.y);
+        re = make_uint2(pr.z, pr.w);
+      }
+      if (__uint_as_float(re.x) < __uint_as_float(le.x)) { child--; re = le; }
+      hset(hole, re);
       hole = child;
     }
     if ((len & 1u) == 0 && child == (len - 2) / 2) {
       child = 2 * (child + 1);
-      heap[hole] = heap[child - 1];
+      hset(hole, hget(child - 1));
       hole = child - 1;
     }
     while (hole > 0) {  // __push_heap of the saved last element
       const uint32_t parent = (hole - 1) >> 1;
-      const uint2 pe = heap[parent];
+      const uint2 pe = hget(parent);
       if (!(__uint_as_float(pe.x) < fv)) break;
-      heap[hole] = pe;
+      hset(hole, pe);
       hole = parent;
     }
-    heap[hole] = value;
+    hset(hole, value);
     return top;
   };
 
@@ -150,8 +171,8 @@ __global__ void __launch_bounds__(512, 1) nbest_lane_kernel(const KModel M, cons
     if (lane == 0) first = atomicAdd(B.work_counter, 32u);
     first = __shfl_sync(0xFFFFFFFFu, first, 0);
     if (first >= B.n) break;
-    const uint32_t sent = first + lane;
-    if (sent < B.n) {
+    if (first + lane < B.n) {
+      const uint32_t sent = B.order ? B.order[first + lane] : first + lane;
       const unsigned long long off = B.offsets[sent];
       const unsigned long long len64 = B.offsets[sent + 1] - off;
       uint32_t n = 0;
@@ -174,19 +195,23 @@ __global__ void __launch_bounds__(512, 1) nbest_lane_kernel(const KModel M, cons
         for (uint32_t p = 0; p < n;) {
           uint32_t mb = one_char_len(text_byte(p));
           if (mb > n - p) mb = n - p;
-          surf[L++] = static_cast<uint16_t>(p);
+          surf[L] = static_cast<uint16_t>(p);
+          maxbt[L] = -INFINITY;
+          ++L;
           p += mb;
         }
         surf[L] = static_cast<uint16_t>(n);
-        // nodes 0 = BOS, 1 = EOS
+        maxbt[L] = -INFINITY;
+        maxbt[0] = 0.f;  // BOS
+        // nodes 0 = BOS, 1 = EOS (EOS's backtrace score is filled in below)
         uint32_t nn = 2;
-        npos[0] = 0; nend[0] = 0; nid[0] = -1; nscore[0] = 0.f; nbt[0] = 0.f; nbb[0] = 0; nbe[0] = 0;
-        npos[1] = static_cast<uint16_t>(L); nend[1] = static_cast<uint16_t>(L); nid[1] = -1; nscore[1] = 0.f; nbt[1] = 0.f;
-        nbb[1] = static_cast<uint16_t>(n); nbe[1] = static_cast<uint16_t>(n);
+        node[0] = make_uint4(0xFFFFFFFFu, 0u, 0u, 0u);
         bool overflow = false;
-        // ---- Model::PopulateNodes ----
+        // ---- Model::PopulateNodes, with Lattice::Viterbi's backtrace scores folded in ----
+        // backtrace(r) = max over nodes q ending where r begins of fl(backtrace(q) + score(r)); fl(x + s) is
+        // monotone in x, so it equals fl(max_q backtrace(q) + score(r)), and every q is complete before r is made.
         for (uint32_t bp = 0; bp < L && !overflow; ++bp) {
-          begin_off[bp] = nn;
+          const float in_bt = maxbt[bp];
           bool has_single = false;
           uint32_t l = root;
           uint32_t clen = 0;  // characters completed so far
@@ -201,122 +226,106 @@ __global__ void __launch_bounds__(512, 1) nbest_lane_kernel(const KModel M, cons
             // get_chars_length (:548-552): characters whose start lies before the piece's end
             const uint32_t length = (kpos + 1 == surf[bp + clen]) ? clen : clen + 1;
             if (nn >= G.node_cap) { overflow = true; break; }
-            npos[nn] = static_cast<uint16_t>(bp);
-            nend[nn] = static_cast<uint16_t>(bp + length);
-            nid[nn] = __ldg(M.trie_id + v);
-            nscore[nn] = kind == kKindUserDefined
-                             ? static_cast<float>(static_cast<double>(__fmul_rn(static_cast<float>(length), M.max_score)) - 0.1)
-                             : __uint_as_float(__ldg(M.trie_val + v));
-            nbt[nn] = 0.f;
-            nbb[nn] = surf[bp];
-            nbe[nn] = surf[bp + length];
+            const float sc = kind == kKindUserDefined
+                                 ? static_cast<float>(static_cast<double>(__fmul_rn(static_cast<float>(length), M.max_score)) - 0.1)
+                                 : __uint_as_float(__ldg(M.trie_val + v));
+            const float bt = __fadd_rn(in_bt, sc);
+            node[nn] = make_uint4(static_cast<uint32_t>(__ldg(M.trie_id + v)), __float_as_uint(sc), __float_as_uint(bt),
+                                  bp | ((bp + length) << 16));
+            maxbt[bp + length] = fmaxf(maxbt[bp + length], bt);
             ++nn;
             has_single |= length == 1;
           }
           if (!has_single && !overflow) {
             if (nn >= G.node_cap) { overflow = true; break; }
-            npos[nn] = static_cast<uint16_t>(bp); nend[nn] = static_cast<uint16_t>(bp + 1);
-            nid[nn] = M.unk_id; nscore[nn] = M.unk_score; nbt[nn] = 0.f;
-            nbb[nn] = surf[bp]; nbe[nn] = surf[bp + 1];
+            const float bt = __fadd_rn(in_bt, M.unk_score);
+            node[nn] = make_uint4(static_cast<uint32_t>(M.unk_id), __float_as_uint(M.unk_score), __float_as_uint(bt),
+                                  bp | ((bp + 1) << 16));
+            maxbt[bp + 1] = fmaxf(maxbt[bp + 1], bt);
             ++nn;
           }
         }
-        begin_off[L] = nn;
-        // end_nodes lists (insertion order): BOS first at position 0
         if (!overflow) {
+          const float eos_bt = __fadd_rn(maxbt[L], 0.f);
+          // end_nodes lists in insertion order (stable counting sort by end character); BOS is the list of 0
           for (uint32_t p = 0; p <= L + 1; ++p) end_off[p] = 0;
-          end_off[0 + 1] += 1;  // BOS
-          for (uint32_t i = 2; i < nn; ++i) end_off[nend[i] + 1] += 1;
+          end_off[0 + 1] += 1;
+          for (uint32_t i = 2; i < nn; ++i) end_off[(node[i].w >> 16) + 1] += 1;
           for (uint32_t p = 0; p <= L; ++p) end_off[p + 1] += end_off[p];
-          // fill using a running cursor kept in begin positions of end_list (stable)
-          // (second pass: place each node at the next free slot of its end position)
-          // use nbt[] as scratch? no: keep a cursor array in the tail of `heap` (unused until A*)
-          for (uint32_t p = 0; p <= L; ++p) heap[p].x = end_off[p];
-          end_list[heap[0].x++] = 0;
-          for (uint32_t i = 2; i < nn; ++i) end_list[heap[nend[i]].x++] = i;
-          // ---- Lattice::Viterbi: backtrace scores ----
-          for (uint32_t pos = 0; pos <= L; ++pos) {
-            const uint32_t rb = pos < L ? begin_off[pos] : 1u, re = pos < L ? begin_off[pos + 1] : 2u;
-            for (uint32_t r = rb; r < re; ++r) {
-              float best = 0.f;
-              bool have_best = false;
-              for (uint32_t q = end_off[pos]; q < end_off[pos + 1]; ++q) {
-                const float sc = __fadd_rn(nbt[end_list[q]], nscore[r]);
-                if (!have_best || sc > best) { best = sc; have_best = true; }
-              }
-              nbt[r] = best;
-            }
+          for (uint32_t p = 0; p <= L; ++p) sort_cur[p] = end_off[p];
+          elist[sort_cur[0]++] = make_uint4(0u, 0u, 0u, 0u);
+          for (uint32_t i = 2; i < nn; ++i) {
+            const uint4 nd = node[i];
+            const uint32_t b = nd.w & 0xFFFFu, e = nd.w >> 16;
+            const bool isunk = static_cast<int32_t>(nd.x) == M.unk_id;
+            const uint32_t contrib = (isunk && bf) ? static_cast<uint32_t>(surf[e] - surf[b]) : 1u;
+            elist[sort_cur[e]++] = make_uint4(i | (b << 16), nd.z, nd.y, contrib | (isunk ? 0x80000000u : 0u));
           }
           // ---- Lattice::NBest: backward A* ----
-          uint32_t pn = 0, hn = 0;
-          hnode[0] = 1; hnext[0] = 0xFFFFFFFFu;  // EOS, next = null
-          hgx[0] = 0.f;
-          hfx[0] = nbt[1];
-          pn = 1;
-          heap_push(hn, 0);
+          uint32_t pn = 1, hn = 0;
+          hyp[0] = make_uint4(0xFFFFFFFFu, 0u, 1u, L);  // EOS: next = null, gx = 0, no ids yet
+          heap_push(hn, make_uint2(__float_as_uint(eos_bt), 0u));
           const uint32_t shrink_to = nbest * 10 < 512 ? nbest * 10 : 512;
           while (hn && !overflow) {
-            const uint32_t top = heap_pop(hn);
-            const uint32_t node = hnode[top];
-            if (node == 0) {  // reached BOS: one result
-              // pass 1: count ids
-              uint32_t cnt = 0;
-              bool prev_unk = false;
-              for (uint32_t h = hnext[top]; hnext[h] != 0xFFFFFFFFu; h = hnext[h]) {
-                const uint32_t nd = hnode[h];
-                const bool isunk = nid[nd] == M.unk_id;
-                if (bf) cnt += isunk ? static_cast<uint32_t>(nbe[nd] - nbb[nd]) : 1u;
-                else cnt += !(isunk && prev_unk);
-                prev_unk = isunk;
-              }
+            const uint2 te = heap_pop(hn);
+            const uint4 th = hyp[te.y];
+            if ((th.z & 0xFFFFu) == 0) {  // reached BOS: one result
+              const uint32_t cnt = th.z >> 16;
               const unsigned long long pos = atomicAdd(O.cursor, static_cast<unsigned long long>(cnt));
               O.cand_start[cbase + K] = pos;
               O.cand_count[cbase + K] = cnt;
-              O.cand_score[cbase + K] = hfx[top];
+              O.cand_score[cbase + K] = __uint_as_float(te.x);
               if (pos + cnt > O.tmp_cap) {
                 atomicOr(O.status + 2, 1u);
                 O.cand_count[cbase + K] = 0;
               } else {
                 uint32_t w = 0;
-                prev_unk = false;
-                for (uint32_t h = hnext[top]; hnext[h] != 0xFFFFFFFFu; h = hnext[h]) {
-                  const uint32_t nd = hnode[h];
-                  const bool isunk = nid[nd] == M.unk_id;
+                bool prev_unk = false;
+                for (uint4 h = hyp[th.x]; h.x != 0xFFFFFFFFu; h = hyp[h.x]) {
+                  const uint4 nd = node[h.z & 0xFFFFu];
+                  const bool isunk = static_cast<int32_t>(nd.x) == M.unk_id;
                   if (isunk) {
                     if (bf) {
-                      for (uint32_t k = nbb[nd]; k < nbe[nd]; ++k) O.tmp_ids[pos + (w++)] = __ldg(M.byte_to_id + text_byte(k));
+                      for (uint32_t k = surf[nd.w & 0xFFFFu]; k < surf[nd.w >> 16]; ++k)
+                        O.tmp_ids[pos + (w++)] = __ldg(M.byte_to_id + text_byte(k));
                     } else if (!prev_unk) {
                       O.tmp_ids[pos + (w++)] = M.unk_id;
                     }
                   } else {
-                    O.tmp_ids[pos + (w++)] = nid[nd];
+                    O.tmp_ids[pos + (w++)] = static_cast<int32_t>(nd.x);
                   }
                   prev_unk = isunk;
                 }
+                if (w != cnt) atomicOr(O.status + 1, 1u);
               }
               if (++K == nbest) break;
               continue;
             }
-            // expand: one hypothesis per node ending where `node` begins, in end_nodes order
-            const uint32_t p0 = npos[node];
-            const float top_gx = hgx[top];
-            for (uint32_t q = end_off[p0]; q < end_off[p0 + 1]; ++q) {
-              const uint32_t ln = end_list[q];
-              if (pn >= G.hyp_cap || hn + 1 >= G.heap_cap - 512u) { overflow = true; break; }
-              hnode[pn] = static_cast<uint16_t>(ln);
-              hnext[pn] = top;
-              hgx[pn] = __fadd_rn(nscore[ln], top_gx);
-              hfx[pn] = __fadd_rn(nbt[ln], top_gx);
-              heap_push(hn, pn);
+            // expand: one hypothesis per node ending where this one begins, in end_nodes order
+            const uint32_t p0 = th.w & 0xFFFFu;
+            const bool top_unk = (th.w >> 16) & 1u;
+            const float top_gx = __uint_as_float(th.y);
+            const uint32_t top_cnt = th.z >> 16;
+            uint32_t q = end_off[p0];
+            const uint32_t qe = end_off[p0 + 1];
+            if (pn + (qe - q) > G.hyp_cap || hn + (qe - q) + 1 >= G.heap_cap - 512u) { overflow = true; break; }
+            uint4 rec = elist[q];
+            for (; q < qe; ++q) {
+              const uint4 nxt = elist[q + 1 < qe ? q + 1 : q];  // issued ahead of the agenda update below
+              const bool isunk = rec.w >> 31;
+              uint32_t cn = top_cnt + (rec.w & 0x7FFFFFFFu);
+              if (!bf && isunk && top_unk) --cn;
+              hyp[pn] = make_uint4(te.y, __float_as_uint(__fadd_rn(__uint_as_float(rec.z), top_gx)),
+                                   (rec.x & 0xFFFFu) | (cn << 16), (rec.x >> 16) | (isunk ? 0x10000u : 0u));
+              heap_push(hn, make_uint2(__float_as_uint(__fadd_rn(__uint_as_float(rec.y), top_gx)), pn));
               ++pn;
+              rec = nxt;
             }
-            if (hn >= 10000u && !overflow) {  // agenda shrink (:481-505): keep the best `shrink_to`
-              // popped in descending order and re-pushed in that order: the heap array becomes that list
-              // (stash them in the unused tail of the hypothesis fx array? no -- use the heap's own tail)
-              uint2 *keep = heap + (G.heap_cap - shrink_to);
-              for (uint32_t i = 0; i < shrink_to; ++i) keep[i].y = heap_pop(hn);
+            if (hn >= 10000u) {  // agenda shrink (:481-505): pop the best `shrink_to`, clear, push them back in that order
+              uint2 *keep = heap + (G.heap_cap + 1 - shrink_to);
+              for (uint32_t i = 0; i < shrink_to; ++i) keep[i] = heap_pop(hn);
               hn = 0;
-              for (uint32_t i = 0; i < shrink_to; ++i) heap_push(hn, keep[i].y);
+              for (uint32_t i = 0; i < shrink_to; ++i) heap_push(hn, keep[i]);
             }
           }
         }
