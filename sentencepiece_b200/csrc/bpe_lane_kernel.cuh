@@ -210,6 +210,7 @@ __global__ void __launch_bounds__(768, 1) encode_bpe_lane_kernel(const KModel M,
       const uint32_t slot = atomicAdd(B.status, 1u);
       B.deferred[2 * slot] = sent;
       B.deferred[2 * slot + 1] = 0;
+      B.sent_count[sent] = 0;  // until a later pass encodes it
       nlog = 0;
     }
     // ---------------- K4: id path of PopulateSentencePieceText over the symbol log ----------------
@@ -269,6 +270,7 @@ __global__ void __launch_bounds__(768, 1) encode_bpe_lane_kernel(const KModel M,
         }
       }
     }
+    lane_drain(B, first, lane);  // K6 (fused host path only)
     __syncwarp();
   }
 }

@@ -71,6 +71,15 @@ struct KBatch {
   // this launch covers sentences ready_base .. ready_base + n, which arrive in pieces of 2^piece_shift
   const uint32_t *ready;
   uint32_t ready_base, piece_shift;
+  // fused host path (drain.cuh): segments of 2^seg_shift sentences are compacted by the warp that finishes them
+  uint32_t seg_shift;
+  uint32_t *seg_done;                 // [segments] groups finished, or null = no in-kernel compaction
+  unsigned long long *seg_total;      // [segments] flag | ids of the segment
+  unsigned long long *seg_prefix;     // [segments] flag | ids up to and including the segment
+  uint32_t *sent_rel;                 // [n] scratch: offset of a sentence's ids inside its segment
+  int32_t *out_ids;                   // result buffers (pinned host memory in the fused path)
+  unsigned long long *out_offsets;    // [n+1]
+  unsigned long long out_cap, out_off_base;
   // outputs of the encode kernel
   int32_t *tmp_ids;              // ids in completion order
   uint32_t *tmp_tok_end;         // (spans) token end offsets in normalized text, same positions

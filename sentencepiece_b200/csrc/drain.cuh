@@ -1,0 +1,138 @@
+// drain.cuh -- K6: in-kernel compaction of finished segments into the caller's result buffers.
+//
+// Fused host path (engine.cu, encode_host_fused): ONE launch of a lane kernel encodes the whole
+// batch.  The ids of a sentence land in a temporary buffer in completion order (K4); the result
+// the reference-facing API returns is ids in INPUT order plus id_offsets[n + 1]
+// (SentencePieceProcessor::Encode over a list, sentencepiece_processor.cc:392-403).  The batch is
+// cut into segments of 2^seg_shift consecutive sentences, each segment is length-ordered among
+// itself (order_kernel.cuh), and the warp that finishes the LAST sentence group of a segment
+// compacts that segment:
+//   1. exclusive scan of the segment's id counts, segment total published;
+//   2. decoupled look-back over the earlier segments' {total, inclusive prefix} words gives the
+//      segment's first output position (all warps are resident, and the work counter hands out
+//      groups in segment order, so every earlier segment is held by a running warp);
+//   3. id_offsets and the ids themselves are written to the result buffers -- pinned host memory
+//      in the fused path, i.e. the compaction IS the device-to-host transfer, overlapped with the
+//      encode of later segments.
+#ifndef SPM_B200_DRAIN_CUH_
+#define SPM_B200_DRAIN_CUH_
+
+#include "device_model.h"
+
+namespace spm_b200 {
+
+constexpr unsigned long long kSegFlag = 1ull << 63;
+
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p) {
+  return *reinterpret_cast<const volatile unsigned long long *>(p);
+}
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
+  return v;
+}
+
+// Called by every warp after it has stored a group's results (sent_start / sent_count / tmp_ids).
+// `first` is the group's position in processing order.
+__device__ __forceinline__ void lane_drain(const KBatch &B, uint32_t first, uint32_t lane) {
+  if (!B.seg_done) return;
+  const uint32_t seg = first >> B.seg_shift;
+  const uint32_t seg_lo = seg << B.seg_shift;
+  const uint32_t seg_n = min(B.n - seg_lo, 1u << B.seg_shift);
+  __threadfence();  // release: this group's results before the counter
+  uint32_t prev = 0;
+  if (lane == 0) prev = atomicAdd(B.seg_done + seg, 1u);
+  prev = __shfl_sync(0xFFFFFFFFu, prev, 0);
+  if (prev + 1 != (seg_n + 31) / 32) return;
+  __threadfence();  // acquire: the other groups' results
+  // ---- 1. scan of the counts; relative offsets parked in sent_rel ----
+  uint32_t run = 0;
+  for (uint32_t j = 0; j < seg_n; j += 32) {
+    const uint32_t i = seg_lo + j + lane;
+    const uint32_t cnt = j + lane < seg_n ? __ldcg(B.sent_count + i) : 0u;
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+      if (lane >= static_cast<uint32_t>(d)) incl += t;
+    }
+    if (j + lane < seg_n) B.sent_rel[i] = run + incl - cnt;
+    run += __shfl_sync(0xFFFFFFFFu, incl, 31);
+  }
+  const unsigned long long total = run;
+  if (lane == 0) {
+    *reinterpret_cast<volatile unsigned long long *>(B.seg_total + seg) = total | kSegFlag;
+    __threadfence();
+  }
+  // ---- 2. decoupled look-back, 32 predecessors per step ----
+  unsigned long long prefix = 0;
+  for (int t = static_cast<int>(seg) - 1; t >= 0;) {
+    const int idx = t - static_cast<int>(lane);
+    unsigned long long pv = kSegFlag, tv = 0;  // a virtual predecessor before segment 0 has prefix 0
+    if (idx >= 0) {
+      pv = ld_volatile_u64(B.seg_prefix + idx);
+      if (!(pv & kSegFlag)) tv = ld_volatile_u64(B.seg_total + idx);
+    }
+    const uint32_t has_p = __ballot_sync(0xFFFFFFFFu, (pv & kSegFlag) != 0);
+    const uint32_t has_any = __ballot_sync(0xFFFFFFFFu, ((pv | tv) & kSegFlag) != 0);
+    const uint32_t first_p = has_p ? static_cast<uint32_t>(__ffs(has_p)) - 1u : 32u;
+    const uint32_t need = first_p >= 32u ? 0xFFFFFFFFu : ((1u << first_p) - 1u);
+    if ((has_any & need) != need) {  // a nearer segment has published nothing yet
+      __nanosleep(100);
+      continue;
+    }
+    unsigned long long mine = 0;
+    if (lane < first_p) mine = tv & ~kSegFlag;
+    else if (lane == first_p) mine = pv & ~kSegFlag;
+    prefix += warp_sum_u64(mine);
+    if (first_p < 32u) break;
+    t -= 32;
+  }
+  if (lane == 0) {
+    *reinterpret_cast<volatile unsigned long long *>(B.seg_prefix + seg) = (prefix + total) | kSegFlag;
+    __threadfence();
+  }
+  // ---- 3. results ----
+  const bool room = prefix + total <= B.out_cap;
+  if (!room) {
+    if (lane == 0) atomicOr(B.status + 2, 2u);
+  }
+  __syncwarp();
+  for (uint32_t j = 0; j < seg_n; j += 32) {
+    const uint32_t i = seg_lo + j + lane;
+    const bool have = j + lane < seg_n;
+    unsigned long long src = 0, dst = 0;
+    uint32_t cnt = 0;
+    if (have) {
+      cnt = __ldcg(B.sent_count + i);
+      src = __ldcg(B.sent_start + i);
+      dst = prefix + __ldcg(B.sent_rel + i);
+      B.out_offsets[i] = B.out_off_base + dst;
+    }
+    if (!room) continue;
+    // one sentence per step: its ids are contiguous on both sides -> coalesced 128-byte loads and stores; four
+    // sentences are in flight at a time so that the loads overlap
+#pragma unroll 1
+    for (uint32_t k = 0; k < 32; k += 4) {
+      unsigned long long s[4], d[4];
+      uint32_t c[4];
+      int32_t v[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        s[q] = __shfl_sync(0xFFFFFFFFu, src, k + q);
+        d[q] = __shfl_sync(0xFFFFFFFFu, dst, k + q);
+        c[q] = __shfl_sync(0xFFFFFFFFu, cnt, k + q);
+        v[q] = lane < c[q] ? __ldcg(B.tmp_ids + s[q] + lane) : 0;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (lane < c[q]) B.out_ids[d[q] + lane] = v[q];
+        for (uint32_t r = 32 + lane; r < c[q]; r += 32) B.out_ids[d[q] + r] = __ldcg(B.tmp_ids + s[q] + r);
+      }
+    }
+  }
+  if (seg_lo + seg_n == B.n && lane == 0) B.out_offsets[B.n] = B.out_off_base + prefix + total;
+}
+
+}  // namespace spm_b200
+#endif

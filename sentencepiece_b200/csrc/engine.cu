@@ -181,6 +181,12 @@ struct spm_engine {
   cudaEvent_t ev_offs = nullptr;
   int encode_host_streamed(const char *bytes, const uint64_t *offsets, size_t n, const int32_t **ids,
                            const uint64_t **id_offsets);
+  int encode_host_fused(const char *bytes, const uint64_t *offsets, size_t n, const int32_t **ids, const uint64_t **id_offsets);
+  bool fused_host_path = true;
+  uint64_t fused_fallbacks = 0;
+  int fused_skip = 0;
+  DevBuf<uint32_t> d_seg_done, d_sent_rel;
+  DevBuf<unsigned long long> d_seg_words;
   // the conditions under which run_device takes a lane kernel for an ids-only batch
   bool uses_lane_kernel() const {
     if (G != 1) return false;
@@ -1065,6 +1071,170 @@ int spm_engine::encode_host_streamed(const char *bytes, const uint64_t *offsets,
   return SPM_OK;
 }
 
+// Large host batches, fused: ONE launch of a lane kernel for the whole batch.  Input streams in as in
+// encode_host_streamed; the results are compacted segment by segment inside the kernel (drain.cuh) straight into the
+// pinned host buffers, so the transfer of the ids overlaps the encode and nothing is left to do after the kernel but
+// read the status words.  Batches the kernel cannot finish on its own (a sentence deferred to the long path, result
+// buffer too small) are redone through encode_host_streamed.
+int spm_engine::encode_host_fused(const char *bytes, const uint64_t *offsets, size_t n, const int32_t **ids,
+                                  const uint64_t **id_offsets) {
+  CUDA_TRY(cudaSetDevice(device));
+  if (!s_h2d) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&s_h2d, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&s_d2h, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; ++k) {
+      CUDA_TRY(cudaEventCreateWithFlags(&ev_in[k], cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&ev_out[k], cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&ev_d2h[k], cudaEventDisableTiming));
+    }
+  }
+  if (!ev_offs) CUDA_TRY(cudaEventCreateWithFlags(&ev_offs, cudaEventDisableTiming));
+  const bool trace = getenv("SPM_B200_TRACE") != nullptr;
+  const auto t_begin = std::chrono::steady_clock::now();
+  auto now_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
+  uint32_t kPieceShift = 15;
+  constexpr uint32_t kSegShift = 10;
+  if (const char *v = getenv("SPM_B200_PIECE_SHIFT")) kPieceShift = std::min(20, std::max(10, atoi(v)));
+  const size_t kPiece = size_t{1} << kPieceShift;
+  const size_t P = (n + kPiece - 1) / kPiece;
+  const size_t S = (n + (size_t{1} << kSegShift) - 1) >> kSegShift;
+  const uint32_t n32 = static_cast<uint32_t>(n);
+  const bool bpe = model.model_type == SPM_BPE;
+  const uint64_t total_bytes = offsets[n] - offsets[0];
+  cudaStream_t st = stream;
+  // ---- buffers ----
+  CUDA_TRY(s_bytes.ensure(total_bytes + 64));
+  CUDA_TRY(s_offsets.ensure(n + 1));
+  CUDA_TRY(d_ready.ensure(4));
+  CUDA_TRY(h_marks.ensure(P + 1));
+  CUDA_TRY(h_id_offsets.ensure(n + 1));
+  CUDA_TRY(h_ids.ensure(std::max<size_t>(h_ids.cap, total_bytes / 2 + 2 * n + 4096)));
+  const unsigned long long tmp_cap = total_bytes + 4ull * n + 1024;
+  CUDA_TRY(d_tmp_ids.ensure(tmp_cap));
+  CUDA_TRY(d_sent_start.ensure(n));
+  CUDA_TRY(d_sent_count.ensure(n));
+  CUDA_TRY(d_sent_rel.ensure(n));
+  CUDA_TRY(d_deferred.ensure(2 * n + 2));
+  CUDA_TRY(d_ctrl32.ensure(16));
+  CUDA_TRY(d_ctrl64.ensure(4));
+  CUDA_TRY(h_ctrl32.ensure(16));
+  CUDA_TRY(h_ctrl64.ensure(4));
+  CUDA_TRY(d_seg_done.ensure(S));
+  CUDA_TRY(d_seg_words.ensure(2 * S));
+  // ---- launch geometry of the lane kernels (as in run_device) ----
+  const int lane_threads = bpe ? std::min(threads, 768) : threads;
+  const uint32_t laneR = trie.max_key_len + 2;
+  const uint32_t smem = static_cast<uint32_t>(kLaneTableBytes + static_cast<size_t>(lane_threads / 32) *
+                                                                    (bpe ? kBpeLaneWarpBytes : laneR * 32 * 8));
+  if (smem > smem_optin) { set_error("shared-memory geometry does not fit"); return SPM_ERR_ARG; }
+  const int grid = sm_count * ctas_per_sm;
+  CUDA_TRY(d_lane_slabs.ensure(static_cast<size_t>(grid) * (lane_threads / 32) * lane_slab_bytes(lane_cap) + 256));
+  // ---- queue the whole input ----
+  CUDA_TRY(cudaMemsetAsync(d_ready.p, 0, sizeof(uint32_t), s_h2d));
+  CUDA_TRY(cudaMemcpyAsync(s_offsets.p, offsets, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s_h2d));
+  CUDA_TRY(cudaEventRecord(ev_offs, s_h2d));
+  if (offsets[n] < offsets[0]) { cudaStreamSynchronize(s_h2d); set_error("offsets must be non-decreasing"); return SPM_ERR_ARG; }
+  std::atomic<int> feed_rc{0};
+  std::thread feeder([&]() {
+    if (cudaSetDevice(device) != cudaSuccess) { feed_rc = 1; return; }
+    uint64_t done_bytes = 0;
+    for (size_t p = 0; p < P; ++p) {
+      const size_t hi = std::min(n, (p + 1) * kPiece);
+      uint64_t cut = offsets[hi] - offsets[0];
+      cut = hi == n ? total_bytes : std::min<uint64_t>(total_bytes, (cut + 127u) & ~uint64_t{127});
+      if (cut > done_bytes &&
+          cudaMemcpyAsync(s_bytes.p + done_bytes, bytes + offsets[0] + done_bytes, cut - done_bytes, cudaMemcpyHostToDevice,
+                          s_h2d) != cudaSuccess) { feed_rc = 1; return; }
+      done_bytes = std::max(done_bytes, cut);
+      h_marks.p[p] = static_cast<uint32_t>(hi);
+      if (cudaMemcpyAsync(d_ready.p, h_marks.p + p, sizeof(uint32_t), cudaMemcpyHostToDevice, s_h2d) != cudaSuccess) {
+        feed_rc = 1;
+        return;
+      }
+    }
+  });
+  struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{feeder};
+  // ---- one launch ----
+  last_launches = 0;
+  last_deferred = 0;
+  CUDA_TRY(cudaStreamWaitEvent(st, ev_offs, 0));
+  CUDA_TRY(cudaMemsetAsync(d_ctrl32.p, 0, 16 * sizeof(uint32_t), st));
+  CUDA_TRY(cudaMemsetAsync(d_ctrl64.p, 0, 4 * sizeof(unsigned long long), st));
+  CUDA_TRY(cudaMemsetAsync(d_seg_done.p, 0, S * sizeof(uint32_t), st));
+  CUDA_TRY(cudaMemsetAsync(d_seg_words.p, 0, 2 * S * sizeof(unsigned long long), st));
+  KModel M = km;
+  M.hot_link = M.hot_val = 0;
+  KBatch B{};
+  B.bytes = s_bytes.p - offsets[0];
+  B.offsets = s_offsets.p;
+  B.n = n32;
+  B.tmp_ids = d_tmp_ids.p;
+  B.tmp_cap = tmp_cap;
+  B.cursor = d_ctrl64.p;
+  B.sent_start = d_sent_start.p;
+  B.sent_count = d_sent_count.p;
+  B.work_counter = d_ctrl32.p + 4;
+  B.deferred = d_deferred.p;
+  B.status = d_ctrl32.p;
+  B.ready = d_ready.p;
+  B.ready_base = 0;
+  B.piece_shift = kPieceShift;
+  B.seg_shift = kSegShift;
+  B.seg_done = d_seg_done.p;
+  B.seg_total = d_seg_words.p;
+  B.seg_prefix = d_seg_words.p + S;
+  B.sent_rel = d_sent_rel.p;
+  {
+    void *dp = nullptr;
+    CUDA_TRY(cudaHostGetDevicePointer(&dp, h_ids.p, 0));
+    B.out_ids = static_cast<int32_t *>(dp);
+    CUDA_TRY(cudaHostGetDevicePointer(&dp, h_id_offsets.p, 0));
+    B.out_offsets = static_cast<unsigned long long *>(dp);
+  }
+  B.out_cap = h_ids.cap;
+  B.out_off_base = 0;
+  CUDA_TRY(cudaEventRecord(ev[0], st));
+  { const int rc = build_order(s_offsets.p, n, st, &B.order, 1u << kSegShift); if (rc) return rc; }
+  if (!B.order) { set_error("fused path needs the segment order"); return SPM_ERR_ARG; }
+  if (bpe) encode_bpe_lane_kernel<<<grid, lane_threads, smem, st>>>(M, B, d_lane_slabs.p, lane_cap);
+  else encode_unigram_lane_kernel<<<grid, lane_threads, smem, st>>>(M, B, d_lane_slabs.p, lane_cap, laneR);
+  CUDA_TRY(cudaGetLastError());
+  ++last_launches;
+  CUDA_TRY(cudaEventRecord(ev[1], st));
+  CUDA_TRY(cudaEventRecord(ev[2], st));
+  CUDA_TRY(cudaMemcpyAsync(h_ctrl32.p, d_ctrl32.p, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  if (trace) fprintf(stderr, "[trace] fused kernel launched at %.3f ms\n", now_ms());
+  // the offsets are checked while the GPU works (a decreasing pair only makes the kernels defer that sentence: the
+  // lengths are taken as unsigned); a bad batch is reported after the launch has drained
+  uint64_t bad = 0;
+  for (size_t i = 0; i < n; ++i) bad |= static_cast<uint64_t>(offsets[i + 1] < offsets[i]);
+  CUDA_TRY(cudaStreamSynchronize(st));
+  feeder.join();
+  if (trace) fprintf(stderr, "[trace] fused kernel done at %.3f ms\n", now_ms());
+  if (bad) { cudaDeviceSynchronize(); set_error("offsets must be non-decreasing"); return SPM_ERR_ARG; }
+  if (feed_rc) { cudaDeviceSynchronize(); set_error("host-to-device copy of a streamed batch failed"); return SPM_ERR_CUDA; }
+  if (h_ctrl32.p[1] & 2u) { set_error("encode failed: the host-to-device copy of a streamed batch made no progress for 3 s"); return SPM_ERR_CUDA; }
+  if (h_ctrl32.p[1]) { set_error("encode failed: internal consistency check (status " + std::to_string(h_ctrl32.p[1]) + ")"); return SPM_ERR_ENCODE; }
+  if (h_ctrl32.p[0] || h_ctrl32.p[2]) {
+    // deferred sentences or a buffer that was too small: the chunked path has the second-chance and retry logic
+    if (trace) fprintf(stderr, "[trace] fused path incomplete (deferred %u, overflow %u): redoing the batch in chunks\n",
+                       h_ctrl32.p[0], h_ctrl32.p[2]);
+    fused_fallbacks++;
+    fused_skip = 8;  // data like this (long words, very long lines) tends to come in runs: go chunked for a while
+    return encode_host_streamed(bytes, offsets, n, ids, id_offsets);
+  }
+  const uint64_t tot = h_id_offsets.p[n];
+  float a = 0.f;
+  if (cudaEventElapsedTime(&a, ev[0], ev[1]) != cudaSuccess) a = 0.f;
+  last_main_ms = a;
+  last_ms = a;
+  last_h2d = total_bytes + (n + 1) * sizeof(uint64_t) + P * sizeof(uint32_t);
+  last_d2h = tot * sizeof(int32_t) + (n + 1) * sizeof(uint64_t);  // written by the kernel over PCIe
+  *ids = h_ids.p;
+  *id_offsets = h_id_offsets.p;
+  return SPM_OK;
+}
+
 // ---- n-best (K5): lattice + A* per sentence on the GPU; leaves candidates in the temporary buffers ----
 int spm_engine::run_nbest(const char *bytes, const uint64_t *offsets, size_t n, uint32_t nbest, uint64_t *tmp_total) {
   cudaStream_t st = stream;
@@ -1181,6 +1351,7 @@ static int create_common(spm_engine *e, int device, spm_engine **out) {
                                                       std::to_string(prop.major) + "." + std::to_string(prop.minor));
   e->sm_count = prop.multiProcessorCount;
   if (const char *v = getenv("SPM_B200_SORT")) e->sort_by_length = atoi(v) != 0;  // A/B knob for profiles/
+  if (const char *v = getenv("SPM_B200_FUSED")) e->fused_host_path = atoi(v) != 0;
   e->smem_optin = prop.sharedMemPerBlockOptin;
   if (cudaSetDevice(device) != cudaSuccess) return fail(SPM_ERR_CUDA, "cudaSetDevice failed");
   int rc = e->build_tables();
@@ -1258,7 +1429,7 @@ void spm_engine_destroy(spm_engine *e) {
     if (e->ev_d2h[k]) cudaEventDestroy(e->ev_d2h[k]);
   }
   e->s_bytes.release(); e->s_offsets.release(); e->d_ready.release(); e->h_marks.release();
-  e->d_order.release(); e->d_order_hist.release();
+  e->d_order.release(); e->d_order_hist.release(); e->d_seg_done.release(); e->d_sent_rel.release(); e->d_seg_words.release();
   if (e->ev_offs) cudaEventDestroy(e->ev_offs);
   if (e->s_h2d) cudaStreamDestroy(e->s_h2d);
   if (e->s_d2h) cudaStreamDestroy(e->s_d2h);
@@ -1437,6 +1608,10 @@ int spm_encode_ids(spm_engine *e, const char *bytes, const uint64_t *offsets, si
                    const uint64_t **id_offsets) {
   if (e && offsets && ids && id_offsets && bytes && n >= e->pipeline_min_sentences && n < 0xFFFFFFF0ull) {
     std::lock_guard<std::mutex> lk(e->mu);
+    if (e->uses_lane_kernel() && e->sort_by_length && e->fused_host_path) {
+      if (e->fused_skip > 0) --e->fused_skip;
+      else return e->encode_host_fused(bytes, offsets, n, ids, id_offsets);
+    }
     if (e->uses_lane_kernel()) return e->encode_host_streamed(bytes, offsets, n, ids, id_offsets);
     return e->encode_host_pipelined(bytes, offsets, n, ids, id_offsets);
   }

@@ -28,6 +28,7 @@
 #define SPM_B200_LANE_KERNEL_CUH_
 
 #include "kernels.cuh"
+#include "drain.cuh"
 
 namespace spm_b200 {
 
@@ -364,6 +365,7 @@ __global__ void __launch_bounds__(1024, 1) encode_unigram_lane_kernel(const KMod
         const uint32_t slot = atomicAdd(B.status, 1u);
         B.deferred[2 * slot] = sent;
         B.deferred[2 * slot + 1] = 0;
+        B.sent_count[sent] = 0;  // until a later pass encodes it
       }
     }
     __syncwarp();
@@ -591,6 +593,7 @@ __global__ void __launch_bounds__(1024, 1) encode_unigram_lane_kernel(const KMod
         }
       }
     }
+    lane_drain(B, first, lane);  // K6 (fused host path only)
     __syncwarp();
   }
 }
