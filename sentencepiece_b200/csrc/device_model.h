@@ -80,6 +80,12 @@ struct KBatch {
   int32_t *out_ids;                   // result buffers (pinned host memory in the fused path)
   unsigned long long *out_offsets;    // [n+1]
   unsigned long long out_cap, out_off_base;
+  // progress of the compaction for the host's DMA loop: segments [0, *drained_upto) are final in out_ids; the warp
+  // that advances the counter stores the id count of that prefix to *host_progress (pinned host memory)
+  uint32_t *seg_copied;               // [segments]
+  uint32_t *drained_upto;
+  unsigned long long *host_progress;
+  unsigned long long *kstats;         // [4] cycles (lane 0 of each warp): input wait, compaction, look-back wait, groups; or null
   // outputs of the encode kernel
   int32_t *tmp_ids;              // ids in completion order
   uint32_t *tmp_tok_end;         // (spans) token end offsets in normalized text, same positions

@@ -11,9 +11,10 @@
 //   2. decoupled look-back over the earlier segments' {total, inclusive prefix} words gives the
 //      segment's first output position (all warps are resident, and the work counter hands out
 //      groups in segment order, so every earlier segment is held by a running warp);
-//   3. id_offsets and the ids themselves are written to the result buffers -- pinned host memory
-//      in the fused path, i.e. the compaction IS the device-to-host transfer, overlapped with the
-//      encode of later segments.
+//   3. id_offsets (to pinned host memory) and the ids (to the device result buffer) are written;
+//   4. the run of finished segments is extended and its id count stored to a pinned host word: the
+//      host polls it and fetches the finished prefix with the copy engine while later segments are
+//      still being encoded (SM stores over PCIe reach only ~25 GB/s, the copy engine ~55 GB/s).
 #ifndef SPM_B200_DRAIN_CUH_
 #define SPM_B200_DRAIN_CUH_
 
@@ -45,6 +46,8 @@ __device__ __forceinline__ void lane_drain(const KBatch &B, uint32_t first, uint
   prev = __shfl_sync(0xFFFFFFFFu, prev, 0);
   if (prev + 1 != (seg_n + 31) / 32) return;
   __threadfence();  // acquire: the other groups' results
+  const long long t_start = clock64();
+  long long t_lb = 0;
   // ---- 1. scan of the counts; relative offsets parked in sent_rel ----
   uint32_t run = 0;
   for (uint32_t j = 0; j < seg_n; j += 32) {
@@ -65,6 +68,7 @@ __device__ __forceinline__ void lane_drain(const KBatch &B, uint32_t first, uint
     __threadfence();
   }
   // ---- 2. decoupled look-back, 32 predecessors per step ----
+  const long long t_lb0 = clock64();
   unsigned long long prefix = 0;
   for (int t = static_cast<int>(seg) - 1; t >= 0;) {
     const int idx = t - static_cast<int>(lane);
@@ -88,6 +92,7 @@ __device__ __forceinline__ void lane_drain(const KBatch &B, uint32_t first, uint
     if (first_p < 32u) break;
     t -= 32;
   }
+  t_lb = clock64() - t_lb0;
   if (lane == 0) {
     *reinterpret_cast<volatile unsigned long long *>(B.seg_prefix + seg) = (prefix + total) | kSegFlag;
     __threadfence();
@@ -132,6 +137,28 @@ __device__ __forceinline__ void lane_drain(const KBatch &B, uint32_t first, uint
     }
   }
   if (seg_lo + seg_n == B.n && lane == 0) B.out_offsets[B.n] = B.out_off_base + prefix + total;
+  if (B.kstats && lane == 0) {
+    atomicAdd(B.kstats + 1, static_cast<unsigned long long>(clock64() - t_start));
+    atomicAdd(B.kstats + 2, static_cast<unsigned long long>(t_lb));
+  }
+  // ---- 4. progress: extend the run of finished segments and tell the host how many ids it may fetch ----
+  if (B.seg_copied) {
+    __threadfence();  // the segment's ids before its flag
+    if (lane == 0) {
+      atomicExch(B.seg_copied + seg, 1u);
+      asm volatile("fence.sc.gpu;" ::: "memory");  // flag store before the counter load (two drainers may meet here)
+      const uint32_t nseg = (B.n + (1u << B.seg_shift) - 1u) >> B.seg_shift;
+      for (;;) {
+        const uint32_t w = atomicAdd(B.drained_upto, 0u);
+        if (w >= nseg || atomicAdd(B.seg_copied + w, 0u) == 0u) break;
+        if (atomicCAS(B.drained_upto, w, w + 1u) == w) {
+          const unsigned long long upto = ld_volatile_u64(B.seg_prefix + w) & ~kSegFlag;
+          __threadfence_system();
+          *reinterpret_cast<volatile unsigned long long *>(B.host_progress) = upto;  // the host keeps the maximum it sees
+        }
+      }
+    }
+  }
 }
 
 }  // namespace spm_b200

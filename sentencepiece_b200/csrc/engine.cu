@@ -178,13 +178,14 @@ struct spm_engine {
   DevBuf<uint64_t> s_offsets;
   DevBuf<uint32_t> d_ready;
   PinBuf<uint32_t> h_marks;
+  PinBuf<unsigned long long> h_progress;
   cudaEvent_t ev_offs = nullptr;
   int encode_host_streamed(const char *bytes, const uint64_t *offsets, size_t n, const int32_t **ids,
                            const uint64_t **id_offsets);
   int encode_host_fused(const char *bytes, const uint64_t *offsets, size_t n, const int32_t **ids, const uint64_t **id_offsets);
   bool fused_host_path = true;
   uint64_t fused_fallbacks = 0;
-  int fused_skip = 0;
+  int fused_skip = 0, fused_backoff = 8;
   DevBuf<uint32_t> d_seg_done, d_sent_rel;
   DevBuf<unsigned long long> d_seg_words;
   // the conditions under which run_device takes a lane kernel for an ids-only batch
@@ -648,7 +649,9 @@ int spm_engine::run_device(const uint8_t *d_bytes_base, const uint64_t *d_offs, 
 
     CUDA_TRY(cudaEventRecord(ev[0], st));
     if (lane_path || bpe_lane_path) {
-      const int rc = build_order(d_offs, n, st, &B.order, cur_ready ? (1u << cur_piece_shift) : 0u);
+      uint32_t seg = cur_ready ? (1u << cur_piece_shift) : 0u;
+      if (const char *v = getenv("SPM_B200_SORT_SEG")) seg = static_cast<uint32_t>(atoi(v));  // experiment knob
+      const int rc = build_order(d_offs, n, st, &B.order, seg);
       if (rc) return rc;
       B.ready = cur_ready;
       B.ready_base = cur_ready_base;
@@ -1116,11 +1119,14 @@ int spm_engine::encode_host_fused(const char *bytes, const uint64_t *offsets, si
   CUDA_TRY(d_sent_rel.ensure(n));
   CUDA_TRY(d_deferred.ensure(2 * n + 2));
   CUDA_TRY(d_ctrl32.ensure(16));
-  CUDA_TRY(d_ctrl64.ensure(4));
+  CUDA_TRY(d_ctrl64.ensure(8));
   CUDA_TRY(h_ctrl32.ensure(16));
-  CUDA_TRY(h_ctrl64.ensure(4));
-  CUDA_TRY(d_seg_done.ensure(S));
+  CUDA_TRY(h_ctrl64.ensure(8));
+  CUDA_TRY(d_seg_done.ensure(2 * S + 4));   // groups finished [S], copied flags [S], drained counter
   CUDA_TRY(d_seg_words.ensure(2 * S));
+  CUDA_TRY(d_ids.ensure(h_ids.cap));
+  CUDA_TRY(h_progress.ensure(8));
+  *reinterpret_cast<volatile unsigned long long *>(h_progress.p) = 0;
   // ---- launch geometry of the lane kernels (as in run_device) ----
   const int lane_threads = bpe ? std::min(threads, 768) : threads;
   const uint32_t laneR = trie.max_key_len + 2;
@@ -1159,8 +1165,8 @@ int spm_engine::encode_host_fused(const char *bytes, const uint64_t *offsets, si
   last_deferred = 0;
   CUDA_TRY(cudaStreamWaitEvent(st, ev_offs, 0));
   CUDA_TRY(cudaMemsetAsync(d_ctrl32.p, 0, 16 * sizeof(uint32_t), st));
-  CUDA_TRY(cudaMemsetAsync(d_ctrl64.p, 0, 4 * sizeof(unsigned long long), st));
-  CUDA_TRY(cudaMemsetAsync(d_seg_done.p, 0, S * sizeof(uint32_t), st));
+  CUDA_TRY(cudaMemsetAsync(d_ctrl64.p, 0, 8 * sizeof(unsigned long long), st));
+  CUDA_TRY(cudaMemsetAsync(d_seg_done.p, 0, (2 * S + 4) * sizeof(uint32_t), st));
   CUDA_TRY(cudaMemsetAsync(d_seg_words.p, 0, 2 * S * sizeof(unsigned long long), st));
   KModel M = km;
   M.hot_link = M.hot_val = 0;
@@ -1186,13 +1192,17 @@ int spm_engine::encode_host_fused(const char *bytes, const uint64_t *offsets, si
   B.sent_rel = d_sent_rel.p;
   {
     void *dp = nullptr;
-    CUDA_TRY(cudaHostGetDevicePointer(&dp, h_ids.p, 0));
-    B.out_ids = static_cast<int32_t *>(dp);
     CUDA_TRY(cudaHostGetDevicePointer(&dp, h_id_offsets.p, 0));
     B.out_offsets = static_cast<unsigned long long *>(dp);
+    CUDA_TRY(cudaHostGetDevicePointer(&dp, h_progress.p, 0));
+    B.host_progress = static_cast<unsigned long long *>(dp);
   }
-  B.out_cap = h_ids.cap;
+  B.out_ids = d_ids.p;
+  B.seg_copied = d_seg_done.p + S;
+  B.drained_upto = d_seg_done.p + 2 * S;
+  B.out_cap = std::min<unsigned long long>(h_ids.cap, d_ids.cap);
   B.out_off_base = 0;
+  B.kstats = trace ? d_ctrl64.p + 4 : nullptr;
   CUDA_TRY(cudaEventRecord(ev[0], st));
   { const int rc = build_order(s_offsets.p, n, st, &B.order, 1u << kSegShift); if (rc) return rc; }
   if (!B.order) { set_error("fused path needs the segment order"); return SPM_ERR_ARG; }
@@ -1203,14 +1213,32 @@ int spm_engine::encode_host_fused(const char *bytes, const uint64_t *offsets, si
   CUDA_TRY(cudaEventRecord(ev[1], st));
   CUDA_TRY(cudaEventRecord(ev[2], st));
   CUDA_TRY(cudaMemcpyAsync(h_ctrl32.p, d_ctrl32.p, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  if (trace) CUDA_TRY(cudaMemcpyAsync(h_ctrl64.p, d_ctrl64.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   if (trace) fprintf(stderr, "[trace] fused kernel launched at %.3f ms\n", now_ms());
   // the offsets are checked while the GPU works (a decreasing pair only makes the kernels defer that sentence: the
   // lengths are taken as unsigned); a bad batch is reported after the launch has drained
   uint64_t bad = 0;
   for (size_t i = 0; i < n; ++i) bad |= static_cast<uint64_t>(offsets[i + 1] < offsets[i]);
+  // fetch the finished prefix of the ids with the copy engine while the kernel is still encoding
+  CUDA_TRY(cudaEventRecord(ev_offs, st));  // (reused) kernel + status copy done
+  unsigned long long seen = 0, copied = 0;
+  const unsigned long long min_copy = 1ull << 20;  // ids per copy: 4 MB
+  for (;;) {
+    const cudaError_t q = cudaEventQuery(ev_offs);
+    if (q != cudaSuccess && q != cudaErrorNotReady) CUDA_TRY(q);
+    const unsigned long long pr = *reinterpret_cast<volatile unsigned long long *>(h_progress.p);
+    if (pr > seen && pr <= h_ids.cap) seen = pr;
+    if (seen - copied >= min_copy) {
+      CUDA_TRY(cudaMemcpyAsync(h_ids.p + copied, d_ids.p + copied, (seen - copied) * sizeof(int32_t), cudaMemcpyDeviceToHost, s_d2h));
+      copied = seen;
+    }
+    if (q == cudaSuccess) break;
+  }
   CUDA_TRY(cudaStreamSynchronize(st));
   feeder.join();
-  if (trace) fprintf(stderr, "[trace] fused kernel done at %.3f ms\n", now_ms());
+  if (trace) fprintf(stderr, "[trace] fused kernel done at %.3f ms; warp-cycles: input wait %.1f M, compaction %.1f M (look-back %.1f M), "
+                     "%llu groups on %d warps\n", now_ms(), h_ctrl64.p[4] * 1e-6, h_ctrl64.p[5] * 1e-6, h_ctrl64.p[6] * 1e-6,
+                     static_cast<unsigned long long>(h_ctrl64.p[7]), grid * (lane_threads / 32));
   if (bad) { cudaDeviceSynchronize(); set_error("offsets must be non-decreasing"); return SPM_ERR_ARG; }
   if (feed_rc) { cudaDeviceSynchronize(); set_error("host-to-device copy of a streamed batch failed"); return SPM_ERR_CUDA; }
   if (h_ctrl32.p[1] & 2u) { set_error("encode failed: the host-to-device copy of a streamed batch made no progress for 3 s"); return SPM_ERR_CUDA; }
@@ -1219,11 +1247,19 @@ int spm_engine::encode_host_fused(const char *bytes, const uint64_t *offsets, si
     // deferred sentences or a buffer that was too small: the chunked path has the second-chance and retry logic
     if (trace) fprintf(stderr, "[trace] fused path incomplete (deferred %u, overflow %u): redoing the batch in chunks\n",
                        h_ctrl32.p[0], h_ctrl32.p[2]);
+    CUDA_TRY(cudaStreamSynchronize(s_d2h));
     fused_fallbacks++;
-    fused_skip = 8;  // data like this (long words, very long lines) tends to come in runs: go chunked for a while
+    // data like this (long words, very long lines) tends to come in runs: go chunked for a while, longer each time
+    fused_skip = fused_backoff;
+    fused_backoff = std::min(fused_backoff * 4, 1 << 16);
     return encode_host_streamed(bytes, offsets, n, ids, id_offsets);
   }
+  fused_backoff = 8;
   const uint64_t tot = h_id_offsets.p[n];
+  if (tot > copied) CUDA_TRY(cudaMemcpyAsync(h_ids.p + copied, d_ids.p + copied, (tot - copied) * sizeof(int32_t), cudaMemcpyDeviceToHost, s_d2h));
+  CUDA_TRY(cudaStreamSynchronize(s_d2h));
+  if (trace) fprintf(stderr, "[trace] ids on host at %.3f ms (%llu of %llu fetched while encoding)\n", now_ms(),
+                     static_cast<unsigned long long>(copied), static_cast<unsigned long long>(tot));
   float a = 0.f;
   if (cudaEventElapsedTime(&a, ev[0], ev[1]) != cudaSuccess) a = 0.f;
   last_main_ms = a;
@@ -1428,7 +1464,7 @@ void spm_engine_destroy(spm_engine *e) {
     if (e->ev_out[k]) cudaEventDestroy(e->ev_out[k]);
     if (e->ev_d2h[k]) cudaEventDestroy(e->ev_d2h[k]);
   }
-  e->s_bytes.release(); e->s_offsets.release(); e->d_ready.release(); e->h_marks.release();
+  e->s_bytes.release(); e->s_offsets.release(); e->d_ready.release(); e->h_marks.release(); e->h_progress.release();
   e->d_order.release(); e->d_order_hist.release(); e->d_seg_done.release(); e->d_sent_rel.release(); e->d_seg_words.release();
   if (e->ev_offs) cudaEventDestroy(e->ev_offs);
   if (e->s_h2d) cudaStreamDestroy(e->s_h2d);

@@ -52,6 +52,7 @@ __device__ __forceinline__ void lane_wait_input(const KBatch &B, uint32_t first,
     if (need > B.n) need = B.n;
     need += B.ready_base;
     const volatile uint32_t *r = B.ready;
+    if (B.kstats) atomicAdd(B.kstats + 3, 1ull);
     if (*r < need) {
       const long long t0 = clock64();
       while (*r < need) {
@@ -61,6 +62,7 @@ __device__ __forceinline__ void lane_wait_input(const KBatch &B, uint32_t first,
           break;
         }
       }
+      if (B.kstats) atomicAdd(B.kstats, static_cast<unsigned long long>(clock64() - t0));
     }
     __threadfence();
   }

@@ -1,0 +1,106 @@
+"""Host-buffer C ABI on large batches: the fused path (one kernel launch, streamed input, in-kernel
+compaction, engine.cu encode_host_fused), its chunked fallback (encode_host_streamed) and the plain
+path must return identical ids; checked against the oracle on a sample.  Needs a B200."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import model_bytes
+from oracle import oracle_py
+
+pytestmark = pytest.mark.gpu
+N = 420_000  # > pipeline_min_sentences (300k): spm_encode_ids takes the large-batch paths
+
+
+def _engine(model, **env):
+    """engine created under the given SPM_B200_* experiment knobs (read at engine creation)"""
+    from sentencepiece_b200 import Engine
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update({k: str(v) for k, v in env.items()})
+    try:
+        return Engine(model_bytes(model))
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def _ragged(buf, offs, rng, extra):
+    """insert empty sentences and the `extra` byte strings at random positions"""
+    raw = buf.tobytes()[: int(offs[-1])]
+    sents = [raw[int(offs[i]):int(offs[i + 1])] for i in range(len(offs) - 1)]
+    for pos in sorted(rng.integers(0, len(sents), size=200).tolist(), reverse=True):
+        sents.insert(pos, b"")
+    for e in extra:
+        sents.insert(int(rng.integers(0, len(sents))), e)
+    lens = np.fromiter((len(s) for s in sents), dtype=np.uint64, count=len(sents))
+    o = np.zeros(len(sents) + 1, dtype=np.uint64)
+    np.cumsum(lens, out=o[1:])
+    return np.frombuffer(b"".join(sents), dtype=np.uint8).copy(), o
+
+
+@pytest.mark.parametrize("model,kind", [("uni32k", "en"), ("mix_bf8k", "mixed"), ("bpe32k", "en")])
+def test_fused_equals_chunked_equals_plain(model, kind, corpus_gen):
+    buf, offs = corpus_gen.fill(kind, 7001, N)
+    fused = _engine(model)
+    a, ao = fused.encode_packed(buf, offs)
+    chunked = _engine(model, SPM_B200_FUSED=0)
+    b, bo = chunked.encode_packed(buf, offs)
+    plain = _engine(model, SPM_B200_FUSED=0, SPM_B200_SORT=0)
+    c, co = plain.encode_packed(buf, offs)
+    assert np.array_equal(ao, bo) and np.array_equal(a, b)
+    assert np.array_equal(ao, co) and np.array_equal(a, c)
+    # twice through the same engine: buffers are reused
+    a2, ao2 = fused.encode_packed(buf, offs)
+    assert np.array_equal(ao, ao2) and np.array_equal(a, a2)
+    om = oracle_py.OracleModel(model_bytes(model))
+    raw = buf.tobytes()
+    for i in range(0, N, 4999):
+        assert a[int(ao[i]):int(ao[i + 1])].tolist() == om.encode(raw[int(offs[i]):int(offs[i + 1])])[0].tolist(), i
+    for e in (fused, chunked, plain):
+        e.close()
+
+
+def test_fused_falls_back_on_long_sentences(corpus_gen):
+    """sentences the lane kernel defers (longer than its slab) make the fused attempt incomplete: the
+    batch is redone in chunks and the result is still exact; empty sentences in between."""
+    rng = np.random.default_rng(5)
+    buf, offs = corpus_gen.fill("en", 7002, N)
+    raw = buf.tobytes()
+    long1 = raw[: 6000]
+    long2 = (b"x" * 3000) + b" " + raw[100:2000]
+    rb, ro = _ragged(buf, offs, rng, [long1, long2])
+    eng = _engine("uni32k")
+    a, ao = eng.encode_packed(rb, ro)
+    ref = _engine("uni32k", SPM_B200_FUSED=0, SPM_B200_SORT=0)
+    b, bo = ref.encode_packed(rb, ro)
+    assert np.array_equal(ao, bo) and np.array_equal(a, b)
+    om = oracle_py.OracleModel(model_bytes("uni32k"))
+    rraw = rb.tobytes()
+    lens = np.diff(ro)
+    check = list(np.nonzero(lens > 2500)[0]) + list(np.nonzero(lens == 0)[0][:5]) + list(range(0, len(lens), 9001))
+    assert len([i for i in check if lens[i] > 2500]) == 2
+    for i in check:
+        i = int(i)
+        assert a[int(ao[i]):int(ao[i + 1])].tolist() == om.encode(rraw[int(ro[i]):int(ro[i + 1])])[0].tolist(), i
+    # the next plain batch goes through the fused path again (or its back-off) and is still exact
+    a3, ao3 = eng.encode_packed(buf, offs)
+    b3, bo3 = ref.encode_packed(buf, offs)
+    assert np.array_equal(ao3, bo3) and np.array_equal(a3, b3)
+    eng.close()
+    ref.close()
+
+
+def test_large_batch_rejects_decreasing_offsets(corpus_gen):
+    buf, offs = corpus_gen.fill("en", 7003, N)
+    bad = offs.copy()
+    bad[1000] = bad[1001] + 5  # offsets[1000] > offsets[1001]
+    eng = _engine("uni32k")
+    with pytest.raises(RuntimeError, match="non-decreasing"):
+        eng.encode_packed(buf, bad)
+    a, ao = eng.encode_packed(buf, offs)  # the engine is still usable
+    assert len(ao) == N + 1 and int(ao[-1]) == len(a)
+    eng.close()
