@@ -33,18 +33,7 @@ __global__ void __launch_bounds__(768, 1) encode_bpe_lane_kernel(const KModel M,
   extern __shared__ __align__(128) uint8_t smem[];
   uint32_t *s_tab = reinterpret_cast<uint32_t *>(smem);
   uint8_t *arrays = smem + kLaneTableBytes;
-  for (uint32_t i = threadIdx.x; i < kLaneTableBytes / 4; i += blockDim.x) {
-    uint32_t v;
-    if (i < 8) v = M.cm_lead[i];
-    else if (i < 8 + 1024) v = M.cm_pair[i - 8];
-    else if (i < 8 + 1024 + 128) v = static_cast<uint32_t>(M.cm_solo[i - 8 - 1024]);
-    else {  // plain ASCII bytes: no charsmap rule starts with them and they are not the space
-      const uint32_t wq = i - (8 + 1024 + 128);
-      v = ~((M.flags & kFlagHasCharsmap) ? M.cm_lead[wq] : 0u);
-      if (wq == 1) v &= ~1u;  // ' ' = 0x20
-    }
-    s_tab[i] = v;
-  }
+  fill_lane_tables(M, s_tab);
   __syncthreads();
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t warp_in_cta = threadIdx.x >> 5;
@@ -66,6 +55,7 @@ __global__ void __launch_bounds__(768, 1) encode_bpe_lane_kernel(const KModel M,
     c.s_pair = s_tab + 8;
     c.s_solo = reinterpret_cast<const int32_t *>(s_tab + 8 + 1024);
     c.s_plain = s_tab + 8 + 1024 + 128;
+    c.s_plainsp = c.s_plain + 4;
   }
   const uint2 *node2 = M.trie_node2;
   const uint32_t root = __ldg(&node2[0]).x;

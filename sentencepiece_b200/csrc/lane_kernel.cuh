@@ -40,7 +40,37 @@ __host__ __device__ inline unsigned long long lane_slab_bytes(uint32_t cap) {
   return (static_cast<unsigned long long>(cap / 4 + kLaneTextSlack) + (cap + 4)) * 32ull * 4ull;
 }
 // shared memory for the normalizer's fast-path tables
-constexpr uint32_t kLaneTableBytes = 32 + 4096 + 512 + 16;  // cm_lead[8] + cm_pair[1024] + cm_solo[128] + plain[4]
+constexpr uint32_t kLaneTableBytes = 32 + 4096 + 512 + 16 + 16;  // cm_lead[8] + cm_pair[1024] + cm_solo[128] + plain[4] + plain_or_space[4]
+
+// Fills the normalizer's fast-path tables in shared memory (all threads of the CTA; caller synchronizes).
+__device__ __forceinline__ void fill_lane_tables(const KModel &M, uint32_t *s_tab) {
+  const bool has_cm = M.flags & kFlagHasCharsmap;
+  for (uint32_t i = threadIdx.x; i < 8 + 1024 + 128 + 4; i += blockDim.x) {
+    uint32_t v;
+    if (i < 8) v = M.cm_lead[i];
+    else if (i < 8 + 1024) v = M.cm_pair[i - 8];
+    else if (i < 8 + 1024 + 128) v = static_cast<uint32_t>(M.cm_solo[i - 8 - 1024]);
+    else {  // plain ASCII bytes: no charsmap rule starts with them and they are not the space
+      const uint32_t wq = i - (8 + 1024 + 128);
+      v = ~(has_cm ? M.cm_lead[wq] : 0u);
+      if (wq == 1) v &= ~1u;  // ' ' = 0x20
+    }
+    s_tab[i] = v;
+  }
+  // "simple" ASCII bytes (space included): followed by another ASCII byte they are always their own chunk -- no
+  // rule is the byte alone or the byte + an ASCII byte.  (nmt_nfkc has letter + combining-mark compositions, so
+  // most letters DO start rules; those need a non-ASCII second byte, which the caller excludes.)
+  for (uint32_t wq = threadIdx.x >> 5; wq < 4; wq += blockDim.x >> 5) {
+    const uint32_t ch = wq * 32 + (threadIdx.x & 31);
+    bool simple = true;
+    if (has_cm && ((M.cm_lead[wq] >> (ch & 31u)) & 1u)) {
+      simple = M.cm_solo[ch] < 0;
+      for (uint32_t q = 0; q < 4; ++q) simple = simple && M.cm_pair[((ch * 256u) >> 5) + q] == 0u;
+    }
+    const uint32_t word = __ballot_sync(0xFFFFFFFFu, simple);
+    if ((threadIdx.x & 31) == 0) s_tab[8 + 1024 + 128 + 4 + wq] = word;
+  }
+}
 
 // Streamed host batches (engine.cu, encode_host_streamed): the batch arrives in pieces of 2^piece_shift
 // sentences and *B.ready counts the sentences whose bytes are in HBM.  Lane 0 of a warp waits for the piece
@@ -77,6 +107,7 @@ struct LaneCtx {
   const uint32_t *s_lead, *s_pair;
   const int32_t *s_solo;
   const uint32_t *s_plain;  // bit b: ASCII byte b is copied verbatim (no rule starts with it, not a space)
+  const uint32_t *s_plainsp;  // bit b: ASCII byte b followed by an ASCII byte is always its own chunk (space included)
 };
 
 // Sequential byte stream over a lane's input: 16-byte aligned chunks (next chunk prefetched)
@@ -161,17 +192,43 @@ __device__ __forceinline__ uint32_t lane_normalize(const KModel &M, const uint8_
   // One chunk of NormalizePrefix (normalizer.cc:195-253) + the emit logic of Normalize (:131-163)
   while (pos < len) {
     const uint32_t rem = len - pos;
-    // ---- fast path: four plain ASCII bytes at once (each is its own identity chunk) ----
+    // ---- fast path: four ASCII bytes at once, each "simple" (its own chunk when an ASCII byte follows) and with
+    //      an ASCII byte (or the end of the sentence) after the window.  Branch-free restatement of :131-163 for
+    //      such chunks: a space after a space is dropped (remove_extra_whitespaces), otherwise it becomes U+2581 or
+    //      stays ' '; the <= 8 output bytes are appended with at most two word stores. ----
     if (started && !has_user && rem >= 4) {
       const uint32_t w4 = static_cast<uint32_t>(S.win);
       const uint32_t c0 = w4 & 0xFFu, c1 = (w4 >> 8) & 0xFFu, c2 = (w4 >> 16) & 0xFFu, c3 = w4 >> 24;
-      if (!(w4 & 0x80808080u) && ((c.s_plain[c0 >> 5] >> (c0 & 31u)) & (c.s_plain[c1 >> 5] >> (c1 & 31u)) &
-                                  (c.s_plain[c2 >> 5] >> (c2 & 31u)) & (c.s_plain[c3 >> 5] >> (c3 & 31u)) & 1u)) {
-        const uint32_t r = (out & 3u) * 8u;
-        if (out + 3 < cap) c.text_w[static_cast<size_t>(out >> 2) * 32] = acc | (w4 << r); else overflow = true;
-        acc = r ? (w4 >> (32u - r)) : 0u;
-        out += 4;
-        is_prev_space = false;
+      if (!(w4 & 0x80808080u) && ((c.s_plainsp[c0 >> 5] >> (c0 & 31u)) & (c.s_plainsp[c1 >> 5] >> (c1 & 31u)) &
+                                  (c.s_plainsp[c2 >> 5] >> (c2 & 31u)) & (c.s_plainsp[c3 >> 5] >> (c3 & 31u)) & 1u) &&
+          (rem == 4 || S.peek(4) < 0x80u)) {
+        unsigned long long chunk = 0;
+        uint32_t clen = 0;
+        bool prev = is_prev_space;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t ch = (w4 >> (8 * i)) & 0xFFu;
+          const bool sp = ch == ' ';
+          const bool emit = !(sp && prev);
+          const uint32_t bytes = (sp && esc) ? 0x8196E2u : ch;  // U+2581 = E2 96 81
+          const uint32_t blen = emit ? ((sp && esc) ? 3u : 1u) : 0u;
+          chunk |= static_cast<unsigned long long>(emit ? bytes : 0u) << (8u * clen);
+          clen += blen;
+          prev = sp && rm;
+        }
+        is_prev_space = prev;
+        const uint32_t r8 = (out & 3u) * 8u;
+        const unsigned long long lo = static_cast<unsigned long long>(acc) | (chunk << r8);
+        const uint32_t hi = r8 ? static_cast<uint32_t>(chunk >> (64u - r8)) : 0u;
+        const uint32_t nw = ((out & 3u) + clen) >> 2;  // full words completed: 0..2
+        if (out <= cap) {
+          uint32_t *wp = c.text_w + static_cast<size_t>(out >> 2) * 32;
+          if (nw >= 1) wp[0] = static_cast<uint32_t>(lo);
+          if (nw >= 2) wp[32] = static_cast<uint32_t>(lo >> 32);
+        }
+        acc = nw == 0 ? static_cast<uint32_t>(lo) : (nw == 1 ? static_cast<uint32_t>(lo >> 32) : hi);
+        out += clen;
+        if (out > cap) overflow = true;
         pos += 4;
         S.consume(4);
         continue;
@@ -309,19 +366,7 @@ __global__ void __launch_bounds__(1024, 1) encode_unigram_lane_kernel(const KMod
   extern __shared__ __align__(128) uint8_t smem[];
   uint32_t *s_tab = reinterpret_cast<uint32_t *>(smem);
   uint8_t *rings = smem + kLaneTableBytes;
-  // normalizer fast-path tables -> shared memory
-  for (uint32_t i = threadIdx.x; i < kLaneTableBytes / 4; i += blockDim.x) {
-    uint32_t v;
-    if (i < 8) v = M.cm_lead[i];
-    else if (i < 8 + 1024) v = M.cm_pair[i - 8];
-    else if (i < 8 + 1024 + 128) v = static_cast<uint32_t>(M.cm_solo[i - 8 - 1024]);
-    else {  // plain ASCII bytes: no charsmap rule starts with them and they are not the space
-      const uint32_t wq = i - (8 + 1024 + 128);
-      v = ~((M.flags & kFlagHasCharsmap) ? M.cm_lead[wq] : 0u);
-      if (wq == 1) v &= ~1u;  // ' ' = 0x20
-    }
-    s_tab[i] = v;
-  }
+  fill_lane_tables(M, s_tab);
   __syncthreads();
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t warp_in_cta = threadIdx.x >> 5;
@@ -338,6 +383,7 @@ __global__ void __launch_bounds__(1024, 1) encode_unigram_lane_kernel(const KMod
     c.s_pair = s_tab + 8;
     c.s_solo = reinterpret_cast<const int32_t *>(s_tab + 8 + 1024);
     c.s_plain = s_tab + 8 + 1024 + 128;
+    c.s_plainsp = c.s_plain + 4;
   }
   const uint2 *node2 = M.trie_node2;
   const uint32_t root = __ldg(&node2[0]).x;

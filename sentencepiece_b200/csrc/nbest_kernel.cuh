@@ -67,18 +67,7 @@ __global__ void __launch_bounds__(THREADS, 1) nbest_lane_kernel(const KModel M, 
                                                                  uint32_t nbest) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint32_t *s_tab = reinterpret_cast<uint32_t *>(smem);
-  for (uint32_t i = threadIdx.x; i < kLaneTableBytes / 4; i += blockDim.x) {
-    uint32_t v;
-    if (i < 8) v = M.cm_lead[i];
-    else if (i < 8 + 1024) v = M.cm_pair[i - 8];
-    else if (i < 8 + 1024 + 128) v = static_cast<uint32_t>(M.cm_solo[i - 8 - 1024]);
-    else {
-      const uint32_t wq = i - (8 + 1024 + 128);
-      v = ~((M.flags & kFlagHasCharsmap) ? M.cm_lead[wq] : 0u);
-      if (wq == 1) v &= ~1u;
-    }
-    s_tab[i] = v;
-  }
+  fill_lane_tables(M, s_tab);
   __syncthreads();
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -90,6 +79,7 @@ __global__ void __launch_bounds__(THREADS, 1) nbest_lane_kernel(const KModel M, 
     c.s_lead = s_tab; c.s_pair = s_tab + 8;
     c.s_solo = reinterpret_cast<const int32_t *>(s_tab + 8 + 1024);
     c.s_plain = s_tab + 8 + 1024 + 128;
+    c.s_plainsp = c.s_plain + 4;
   }
   // agenda top: [warp][entry][lane]
   uint2 *s_top = reinterpret_cast<uint2 *>(smem + kLaneTableBytes) + static_cast<size_t>(threadIdx.x >> 5) * (32 * TOP) + lane;
