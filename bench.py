@@ -35,6 +35,7 @@ WORKLOADS = {
     "unigram32k_en": ("uni32k", "en", "32k-vocab unigram Viterbi encode, synthetic ~128-byte English sentences"),
     "bpe32k_en": ("bpe32k", "en", "32k-vocab BPE merge encode, synthetic ~128-byte English sentences"),
     "bytefallback_mixed": ("mix_bf8k", "mixed", "byte-fallback unigram + NFKC on mixed CJK/emoji synthetic corpus"),
+    "decode_unigram32k_en": ("uni32k", "en", "Decode(ids) -> text of the ids of the unigram32k_en workload (the step after the path)"),
     "sample_nbest64_en": ("uni32k", "en", "unigram SampleEncode nbest=64 alpha=0.5 (subword regularization lattice), "
                           "256k synthetic English sentences"),
 }
@@ -164,6 +165,92 @@ def run_reference_arm(args, rank, world):
     }))
 
 
+def run_decode_workload(args, eng, rank, world, local_rank, mb):
+    """Decode(ids) -> text for the id lists of the headline workload, through spm_decode_ids with
+    host buffers (ids in the engine's pinned result buffer of a preceding encode; text comes back in pinned memory).
+    `value` = device time of the engine's kernels, `e2e` = wall clock of the synchronous call incl. both copies."""
+    import ctypes
+    import torch
+    import torch.distributed as dist
+    import corpus
+    n = args.sentences
+    g = corpus.CorpusGen()
+    buf, offs = g.fill("en", CORPUS_SEED, n, first=rank * n)
+    ids, ido = eng.encode_packed(buf, offs)          # host copies of the ids: the decode input
+    total_ids = int(ido[-1])
+    lib = eng._lib
+    text_p, to_p = ctypes.c_void_p(), ctypes.c_void_p()
+
+    def step():
+        rc = lib.spm_decode_ids(eng._h, ids.ctypes.data, ido.ctypes.data, n, ctypes.byref(text_p), ctypes.byref(to_p))
+        if rc:
+            raise RuntimeError(lib.spm_last_error(eng._h).decode())
+    for _ in range(max(3, args.warmup)):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    kernel_ms, main_ms, launches = 0.0, 0.0, 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+        info = eng.info()
+        kernel_ms += info.last_kernel_ms
+        main_ms += info.last_main_kernel_ms
+        launches += info.last_kernel_launches
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    clocks = sampler.stop()
+    to = np.ctypeslib.as_array(ctypes.cast(to_p, ctypes.POINTER(ctypes.c_uint64)), (n + 1,))
+    text_bytes = int(to[n])
+    if world > 1:
+        t = torch.tensor([dt, kernel_ms, main_ms], device=torch.device("cuda", local_rank))
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt, kernel_ms, main_ms = (float(x) for x in t.tolist())
+    if rank != 0:
+        return
+    cpu = None
+    if not args.no_cpu:
+        from oracle import oracle_py
+        if oracle_py.ref_available():
+            sample = min(n, 400000)
+            threads = os.cpu_count() or 1
+            rm = oracle_py.RefModel(mb)
+            t1 = time.perf_counter()
+            rm.decode_batch(ids[: int(ido[sample])], ido[: sample + 1], threads=threads)
+            d1 = time.perf_counter() - t1
+            cpu = {"value": sample / d1, "unit": "sentences/s", "cores": threads, "kind": "reference",
+                   "sample": f"first {sample} id lists, {threads} std::threads over SentencePieceProcessor::Decode (oracle/_ref)"}
+    alg = 4 * total_ids + text_bytes + 16 * n   # ids + text + one offset each way
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0) or 6650.0)
+    ach = alg / (main_ms / args.steps * 1e-3) / 1e9
+    print(json.dumps({
+        "metric": "sentences_per_sec", "value": world * n * args.steps / (kernel_ms / 1e3), "unit": "sentences/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": kernel_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32 ids / u8 text", "data": "synthetic",
+        "config": {"workload": args.workload, "model": "uni32k.model", "id_lists_per_gpu_per_step": n,
+                   "ids_per_list": total_ids / n, "text_bytes_per_list": text_bytes / n,
+                   "l2": "inputs+outputs per step exceed the 126 MB L2"},
+        "clocks": clocks,
+        "e2e": {"value": world * n * args.steps / dt, "unit": "sentences/s", "ms_per_step": dt / args.steps * 1e3,
+                "h2d_bytes_per_step": int(eng.info().last_h2d_bytes), "d2h_bytes_per_step": int(eng.info().last_d2h_bytes)},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": ach, "peak": peak or None, "unit": "GB/s", "frac": (ach / peak) if peak else None,
+                     "traffic": None, "kernel": "decode_warp_kernel", "kernel_ms": main_ms / args.steps,
+                     "algorithmic_bytes_per_launch": alg,
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback (B200_PROFILING.md)"},
+        "cpu_baseline": cpu}))
+    eng.close()
+
+
 def run_sample_workload(args, eng, rank, world, local_rank, mb):
     """BASELINE.json configs[4]: SampleEncode(nbest_size=64, alpha=0.5) on 256k sentences.  The path goes through
     the host-buffer C ABI only (n-best on the GPU, the seeded draw on the host), so `value` is the device time of
@@ -273,6 +360,9 @@ def main():
     lib = _capi.load()
     if args.workload == "sample_nbest64_en":
         run_sample_workload(args, eng, rank, world, local_rank, mb)
+        return
+    if args.workload == "decode_unigram32k_en":
+        run_decode_workload(args, eng, rank, world, local_rank, mb)
         return
 
     # ---- this rank's shard, generated straight into pinned host memory ----

@@ -153,6 +153,23 @@ int spm_set_random_seed(spm_engine *e, uint32_t seed);
 int spm_sample_encode_ids(spm_engine *e, const char *bytes, const uint64_t *offsets, size_t n, int nbest_size,
                           float alpha, const int32_t **ids, const uint64_t **id_offsets);
 
+/* Replaces SentencePieceProcessor::Decode(const std::vector<int>& ids, std::string* detokenized)
+ * (src/sentencepiece_processor.cc:911-925 -> :765-909), one call for n id lists: `ids` is the packed
+ * concatenation, id_offsets[n+1] delimits the lists (exactly what spm_encode_ids returns).  Outputs
+ * (engine-owned pinned memory, valid until the next call on this engine): the concatenated UTF-8
+ * text and text_offsets[n+1].  CONTROL pieces are invisible, UNKNOWN pieces become the model's
+ * unk_surface, the leading U+2581 rule of add_dummy_prefix / remove_extra_whitespaces and the
+ * UTF-8 reassembly of BYTE pieces (U+FFFD per invalid byte) follow the reference bit for bit.
+ * Errors like the reference: an id outside [0, vocab) fails the call (SPM_ERR_ARG, "Invalid id: N").
+ * Not on the device path: models with a denormalizer_spec charsmap (SPM_ERR_UNSUPPORTED) and
+ * decode_extra_options (a host-side reordering the caller applies to the id lists). */
+int spm_decode_ids(spm_engine *e, const int32_t *ids, const uint64_t *id_offsets, size_t n, const char **text,
+                   const uint64_t **text_offsets);
+
+/* TrainerSpec.unk_surface (src/sentencepiece_model.proto:228, read at sentencepiece_processor.cc:771-773) for
+ * engines created from an spm_model_desc; engines created from a serialized ModelProto take it from the proto. */
+int spm_engine_set_unk_surface(spm_engine *e, const char *surface, size_t bytes);
+
 /* Pinned host memory helpers for callers that want zero staging copies. */
 void *spm_host_alloc(size_t bytes);
 void spm_host_free(void *p);

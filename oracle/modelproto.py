@@ -54,7 +54,7 @@ def parse_model(data):
     m = dict(pieces=[], scores=[], types=[], model_type=UNIGRAM, byte_fallback=False,
              treat_whitespace_as_suffix=False, unk_piece=b"<unk>", charsmap=b"",
              add_dummy_prefix=True, remove_extra_whitespaces=True, escape_whitespaces=True,
-             self_test=[], has_normalizer_spec=False)
+             self_test=[], has_normalizer_spec=False, unk_surface=" \u2047 ".encode(), denormalizer_charsmap=b"")
     for fno, wt, v in _fields(data):
         if fno == 1 and wt == 2:  # SentencePiece
             piece, score, typ = b"", 0.0, NORMAL
@@ -78,6 +78,8 @@ def parse_model(data):
                     m["treat_whitespace_as_suffix"] = bool(v2)
                 elif f2 == 45:
                     m["unk_piece"] = bytes(v2)
+                elif f2 == 44:
+                    m["unk_surface"] = bytes(v2)
         elif fno == 3 and wt == 2:  # NormalizerSpec
             m["has_normalizer_spec"] = True
             for f2, w2, v2 in _fields(v):
@@ -89,6 +91,10 @@ def parse_model(data):
                     m["remove_extra_whitespaces"] = bool(v2)
                 elif f2 == 5:
                     m["escape_whitespaces"] = bool(v2)
+        elif fno == 5 and wt == 2:  # denormalizer_spec (NormalizerSpec)
+            for f2, w2, v2 in _fields(v):
+                if f2 == 2:
+                    m["denormalizer_charsmap"] = bytes(v2)
         elif fno == 4 and wt == 2:  # SelfTestData
             for f2, w2, v2 in _fields(v):
                 if f2 == 1:

@@ -107,6 +107,8 @@ class OracleModel:
         self.h = L.oracle_create(ctypes.byref(d), err, 256)
         if not self.h:
             raise ValueError("oracle_create: " + err.value.decode())
+        L.oracle_set_unk_surface.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_size_t]
+        L.oracle_set_unk_surface(self.h, m["unk_surface"], len(m["unk_surface"]))
 
     def __del__(self):
         if getattr(self, "h", None):
@@ -229,6 +231,28 @@ class OracleModel:
         return a, ido
 
 
+    def decode_batch(self, ids, ido):
+        """Decode(ids) per list -> (text uint8[], text_offsets uint64[n+1])"""
+        L = self.lib
+        L.oracle_decode_ids.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p),
+                                        ctypes.POINTER(ctypes.c_size_t)]
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        n = len(ido) - 1
+        parts = []
+        to = np.zeros(n + 1, dtype=np.uint64)
+        for i in range(n):
+            a, b = int(ido[i]), int(ido[i + 1])
+            out = ctypes.c_void_p()
+            ln = ctypes.c_size_t()
+            rc = L.oracle_decode_ids(self.h, ids.ctypes.data + 4 * a, b - a, ctypes.byref(out), ctypes.byref(ln))
+            if rc:
+                raise RuntimeError(f"oracle_decode_ids failed ({rc}) at list {i}")
+            parts.append(ctypes.string_at(out, ln.value))
+            L.oracle_free(out)
+            to[i + 1] = to[i] + np.uint64(ln.value)
+        return np.frombuffer(b"".join(parts), dtype=np.uint8), to
+
+
 class RefModel:
     """The unmodified reference through oracle/ref_shim.cc."""
 
@@ -286,6 +310,22 @@ class RefModel:
         buf, offs = pack([s])
         ids, _ = self.encode_batch(buf, offs)
         return ids
+
+    def decode_batch(self, ids, ido, threads=1):
+        L = self.lib
+        L.ref_decode_ids.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int,
+                                     ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p]
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        ido = np.ascontiguousarray(ido, dtype=np.uint64)
+        n = len(ido) - 1
+        to = np.zeros(n + 1, dtype=np.uint64)
+        out = ctypes.c_void_p()
+        rc = L.ref_decode_ids(self.h, ids.ctypes.data, ido.ctypes.data, n, threads, ctypes.byref(out), to.ctypes.data)
+        if rc:
+            raise RuntimeError(f"reference Decode failed at list {rc - 1}")
+        text = np.frombuffer(ctypes.string_at(out, int(to[n])), dtype=np.uint8)
+        L.ref_free_buf(out)
+        return text, to
 
     def encode_count(self, buf, offs, threads):
         buf = np.ascontiguousarray(buf, dtype=np.uint8)

@@ -171,6 +171,37 @@ int ref_piece_size(void *h) {
   return static_cast<SentencePieceProcessor *>(h)->GetPieceSize();
 }
 
+// SentencePieceProcessor::Decode(const std::vector<int>&, std::string*) over a packed batch of id lists.
+// Outputs: *text_out malloc'ed (concatenated), text_offsets[n+1] caller-provided.  Returns 0, or k+1 if list k failed.
+int ref_decode_ids(void *h, const int32_t *ids, const uint64_t *id_offs, size_t n, int nthreads, char **text_out,
+                   uint64_t *text_offsets) {
+  auto *sp = static_cast<SentencePieceProcessor *>(h);
+  std::vector<std::string> outs(n);
+  std::atomic<size_t> next{0};
+  std::atomic<size_t> failed{0};
+  if (nthreads < 1) nthreads = 1;
+  auto work = [&]() {
+    size_t i;
+    while ((i = next.fetch_add(1)) < n) {
+      std::vector<int> v(ids + id_offs[i], ids + id_offs[i + 1]);
+      if (!sp->Decode(v, &outs[i]).ok()) failed.store(i + 1);
+    }
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < nthreads; ++t) th.emplace_back(work);
+  work();
+  for (auto &t : th) t.join();
+  if (failed.load()) return static_cast<int>(failed.load());
+  uint64_t total = 0;
+  for (size_t i = 0; i < n; ++i) { text_offsets[i] = total; total += outs[i].size(); }
+  text_offsets[n] = total;
+  char *buf = static_cast<char *>(malloc(total ? total : 1));
+  for (size_t i = 0; i < n; ++i)
+    if (!outs[i].empty()) memcpy(buf + text_offsets[i], outs[i].data(), outs[i].size());
+  *text_out = buf;
+  return 0;
+}
+
 }  // extern "C"
 
 // ---- n-best / sampling (config 5) -------------------------------------------------

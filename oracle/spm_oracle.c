@@ -168,6 +168,8 @@ struct oracle_model {
   size_t cm_nunits;
   const char *cm_targets;
   size_t cm_targets_len;
+  char *unk_surface; /* Decode: TrainerSpec.unk_surface */
+  size_t unk_surface_len;
 };
 
 void oracle_free(void *p) { free(p); }
@@ -283,6 +285,7 @@ void oracle_destroy(oracle_model *m) {
   if (!m) return;
   ht_free(&m->pieces); ht_free(&m->reserved); ht_free(&m->user);
   free(m->piece_bytes); free(m->piece_off); free(m->scores); free(m->types); free(m->charsmap);
+  free(m->unk_surface);
   free(m);
 }
 
@@ -1015,5 +1018,107 @@ int oracle_sample_encode_batch(const oracle_model *m, const char *bytes, const u
   }
   id_offsets[n] = total;
   *ids_out = all;
+  return 0;
+}
+
+
+/* ------------------------------------------------------------------------------------------------
+ * SentencePieceProcessor::Decode(const std::vector<int>&, SentencePieceText*) -- text only
+ * (src/sentencepiece_processor.cc:765-925).
+ * ---------------------------------------------------------------------------------------------- */
+void oracle_set_unk_surface(oracle_model *m, const char *s, size_t len) {
+  free(m->unk_surface);
+  m->unk_surface = (char *)malloc(len + 1);
+  memcpy(m->unk_surface, s, len);
+  m->unk_surface[len] = 0;
+  m->unk_surface_len = strlen(m->unk_surface); /* the reference takes c_str() (:772-773) */
+}
+
+/* PieceToByte, src/model_interface.cc:214-230: exactly "<0xXX>" with upper-case hex digits */
+static int piece_to_byte(const char *p, size_t len) {
+  if (len != 6 || p[0] != '<' || p[1] != '0' || p[2] != 'x' || p[5] != '>') return -1;
+  int v = 0;
+  for (int i = 3; i < 5; ++i) {
+    const char ch = p[i];
+    int d;
+    if (ch >= '0' && ch <= '9') d = ch - '0';
+    else if (ch >= 'A' && ch <= 'F') d = ch - 'A' + 10;
+    else return -1;
+    v = v * 16 + d;
+  }
+  return v;
+}
+
+typedef struct { char *p; size_t n, cap; } obuf;
+static void obuf_put(obuf *b, const char *s, size_t len) {
+  if (b->n + len + 1 > b->cap) {
+    b->cap = (b->n + len + 1) * 2 + 64;
+    b->p = (char *)realloc(b->p, b->cap);
+  }
+  memcpy(b->p + b->n, s, len);
+  b->n += len;
+}
+
+int oracle_decode_ids(const oracle_model *m, const int32_t *ids, size_t n, char **text_out, size_t *text_len) {
+  static const char kDefaultUnk[] = " \xE2\x81\x87 ";    /* kDefaultUnknownSymbol, :52 */
+  static const char kReplacement[] = "\xEF\xBF\xBD";     /* kReplacementCharacter, :55 */
+  static const char kSpace[] = "\xE2\x96\x81";           /* kSpaceSymbol */
+  const char *unk_surface = m->unk_surface ? m->unk_surface : kDefaultUnk;
+  const size_t unk_len = m->unk_surface ? m->unk_surface_len : sizeof(kDefaultUnk) - 1;
+  obuf text = {0, 0, 0};
+  obuf_put(&text, "", 0);
+  for (size_t i = 0; i < n; ++i)
+    if (ids[i] < 0 || ids[i] >= m->vocab_size) { free(text.p); return 1; }   /* :915-918 */
+  unsigned char *bytes = (unsigned char *)malloc(n + 1);
+  size_t nbytes = 0;        /* pending run of BYTE pieces (:836-876, flushed before the next other piece) */
+  int is_bos_ws = 1, bos_ws_seen = 0;  /* :879-880 */
+  int rc = 0;
+  for (size_t i = 0; i <= n && !rc; ++i) {
+    const int is_byte = i < n && m->types[ids[i]] == ORACLE_BYTE;
+    if (is_byte) {
+      const int32_t id = ids[i];
+      const int b = piece_to_byte(m->piece_bytes + m->piece_off[id], m->piece_off[id + 1] - m->piece_off[id]);
+      if (b < 0) { rc = 2; break; }
+      bytes[nbytes++] = (unsigned char)b;
+      continue;
+    }
+    /* ProcessBytePieces: one Unicode character at a time; an invalid byte becomes U+FFFD */
+    size_t off = 0;
+    while (off < nbytes) {
+      size_t consumed = 0;
+      if (!is_valid_decode_utf8(bytes + off, nbytes - off, &consumed)) {
+        obuf_put(&text, kReplacement, 3);
+        consumed = 1;
+      } else {
+        obuf_put(&text, (const char *)bytes + off, consumed);
+      }
+      off += consumed;
+    }
+    nbytes = 0;
+    if (i == n) break;
+    if (bos_ws_seen || text.n != 0) is_bos_ws = 0;   /* :887 */
+    const int32_t id = ids[i];
+    const char *piece = m->piece_bytes + m->piece_off[id];
+    size_t plen = m->piece_off[id + 1] - m->piece_off[id];
+    const uint8_t type = m->types[id];
+    /* DecodeSentencePiece (:779-812) */
+    if (type == ORACLE_CONTROL) { bos_ws_seen = 0; continue; }
+    if (type == ORACLE_UNKNOWN) { obuf_put(&text, unk_surface, unk_len); bos_ws_seen = 0; continue; }
+    int has_bos_ws = 0;
+    if (is_bos_ws && (m->add_dummy_prefix || m->remove_extra_whitespaces)) {
+      if (plen >= 3 && memcmp(piece, kSpace, 3) == 0) { piece += 3; plen -= 3; has_bos_ws = 1; }
+      if (m->remove_extra_whitespaces) has_bos_ws = 0;
+    }
+    for (size_t k = 0; k < plen;) {   /* StrReplaceAll(piece, {{kSpaceSymbol, " "}}) */
+      if (k + 3 <= plen && memcmp(piece + k, kSpace, 3) == 0) { obuf_put(&text, " ", 1); k += 3; }
+      else { obuf_put(&text, piece + k, 1); k += 1; }
+    }
+    bos_ws_seen = has_bos_ws;
+  }
+  free(bytes);
+  if (rc) { free(text.p); return rc; }
+  text.p[text.n] = 0;
+  *text_out = text.p;
+  *text_len = text.n;
   return 0;
 }

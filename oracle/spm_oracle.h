@@ -95,6 +95,15 @@ int oracle_sample_pick(oracle_mt19937 *g, const float *scores, size_t k, float a
 int oracle_sample_encode_batch(const oracle_model *m, const char *bytes, const uint64_t *offs, size_t n, int nbest_size,
                                float alpha, uint32_t seed, int32_t **ids, uint64_t *id_offsets);
 
+/* ---- next row: SentencePieceProcessor::Decode(ids) -> text
+ * (src/sentencepiece_processor.cc:765-925): IdToPiece, CONTROL pieces invisible, UNKNOWN -> unk_surface, the first
+ * U+2581 stripped while the text is still empty (add_dummy_prefix / remove_extra_whitespaces), U+2581 -> ' ', runs of
+ * BYTE pieces reassembled into UTF-8 with U+FFFD for every structurally invalid byte.  No denormalizer, no
+ * decode_extra_options.  *text is malloc'ed.  Returns 0, 1 for an id out of range (kOutOfRange), 2 for a BYTE piece
+ * that is not "<0xXX>". */
+void oracle_set_unk_surface(oracle_model *m, const char *s, size_t len); /* TrainerSpec.unk_surface, default " \xE2\x81\x87 " */
+int oracle_decode_ids(const oracle_model *m, const int32_t *ids, size_t n, char **text, size_t *text_len);
+
 void oracle_free(void *p);
 
 #ifdef __cplusplus

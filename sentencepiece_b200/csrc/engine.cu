@@ -33,6 +33,7 @@
 #include "lane_kernel.cuh"
 #include "model_reader.h"
 #include "order_kernel.cuh"
+#include "decode_kernel.cuh"
 #include "nbest_kernel.cuh"
 #include "trie_builder.h"
 #include "unigram_warp.cuh"
@@ -195,6 +196,15 @@ struct spm_engine {
       return (km.flags & kFlagBpeWordSplit) && (km.flags & kFlagEscapeWs) && !(km.flags & (kFlagHasUserSymbols | kFlagHasUnused));
     return trie.max_key_len <= 62;
   }
+  // Decode (K7): per-id decoded strings, built on first use
+  DevBuf<uint32_t> d_dec_off, d_dec_info;
+  DevBuf<uint8_t> d_dec_bytes, d_dec_tmp, d_dec_text;
+  DevBuf<int32_t> d_dec_ids;
+  DevBuf<unsigned long long> d_dec_text_offsets;
+  PinBuf<char> h_dec_text;
+  PinBuf<uint64_t> h_dec_text_offsets;
+  bool dec_ready = false;
+  int ensure_decode_tables();
   // n-best / sampling
   DevBuf<uint8_t> d_nb_scratch;
   DevBuf<unsigned long long> d_cand_start, d_cand_offsets;
@@ -1271,6 +1281,51 @@ int spm_engine::encode_host_fused(const char *bytes, const uint64_t *offsets, si
   return SPM_OK;
 }
 
+// ---- Decode (K7): per-id decoded strings + info words (decode_kernel.cuh) ----
+int spm_engine::ensure_decode_tables() {
+  if (dec_ready) return SPM_OK;
+  const int V = model.vocab_size();
+  std::vector<uint32_t> off(V + 1, 0), info(V, 0);
+  std::string bytes;
+  static const char kSpace[] = "\xE2\x96\x81";
+  for (int i = 0; i < V; ++i) {
+    const char *p = model.piece(i);
+    const size_t len = model.piece_len(i);
+    const uint8_t t = model.types[i];
+    off[i] = static_cast<uint32_t>(bytes.size());
+    if (t == SPM_CONTROL) {
+      info[i] = kDecKindControl;
+    } else if (t == SPM_UNKNOWN) {
+      info[i] = kDecKindUnknown;
+      bytes.append(model.unk_surface.c_str());  // the reference takes c_str() (:772-773)
+    } else if (t == SPM_BYTE) {
+      // PieceToByte (model_interface.cc:214-230): exactly "<0xXX>", upper-case hex
+      int v = -1;
+      if (len == 6 && p[0] == '<' && p[1] == '0' && p[2] == 'x' && p[5] == '>') {
+        auto hex = [](char ch) { return ch >= '0' && ch <= '9' ? ch - '0' : (ch >= 'A' && ch <= 'F' ? ch - 'A' + 10 : -1); };
+        const int hi = hex(p[3]), lo = hex(p[4]);
+        if (hi >= 0 && lo >= 0) v = hi * 16 + lo;
+      }
+      info[i] = kDecKindByte | (v < 0 ? kDecBadByte : (static_cast<uint32_t>(v) << kDecByteShift));
+      bytes.push_back(static_cast<char>(v < 0 ? 0 : v));
+    } else {  // NORMAL, USER_DEFINED, UNUSED: U+2581 -> ' ' (StrReplaceAll, :809)
+      info[i] = kDecKindNormal | ((len >= 3 && memcmp(p, kSpace, 3) == 0) ? kDecLeadWs : 0u);
+      for (size_t k = 0; k < len;) {
+        if (k + 3 <= len && memcmp(p + k, kSpace, 3) == 0) { bytes.push_back(' '); k += 3; }
+        else { bytes.push_back(p[k]); k += 1; }
+      }
+    }
+  }
+  off[V] = static_cast<uint32_t>(bytes.size());
+  std::vector<uint8_t> b(bytes.begin(), bytes.end());
+  b.push_back(0);
+  CUDA_TRY(d_dec_off.upload(off));
+  CUDA_TRY(d_dec_info.upload(info));
+  CUDA_TRY(d_dec_bytes.upload(b));
+  dec_ready = true;
+  return SPM_OK;
+}
+
 // ---- n-best (K5): lattice + A* per sentence on the GPU; leaves candidates in the temporary buffers ----
 int spm_engine::run_nbest(const char *bytes, const uint64_t *offsets, size_t n, uint32_t nbest, uint64_t *tmp_total) {
   cudaStream_t st = stream;
@@ -1465,6 +1520,8 @@ void spm_engine_destroy(spm_engine *e) {
     if (e->ev_d2h[k]) cudaEventDestroy(e->ev_d2h[k]);
   }
   e->s_bytes.release(); e->s_offsets.release(); e->d_ready.release(); e->h_marks.release(); e->h_progress.release();
+  e->d_dec_off.release(); e->d_dec_info.release(); e->d_dec_bytes.release(); e->d_dec_tmp.release(); e->d_dec_text.release();
+  e->d_dec_ids.release(); e->d_dec_text_offsets.release(); e->h_dec_text.release(); e->h_dec_text_offsets.release();
   e->d_order.release(); e->d_order_hist.release(); e->d_seg_done.release(); e->d_sent_rel.release(); e->d_seg_words.release();
   if (e->ev_offs) cudaEventDestroy(e->ev_offs);
   if (e->s_h2d) cudaStreamDestroy(e->s_h2d);
@@ -1488,6 +1545,124 @@ int spm_engine_set_types(spm_engine *e, const uint8_t *types) {
   }
   e->model.types.assign(types, types + e->model.vocab_size());
   return e->upload_types();
+}
+
+static void finish_timing(spm_engine *e);
+
+int spm_engine_set_unk_surface(spm_engine *e, const char *surface, size_t bytes) {
+  if (!e || (!surface && bytes)) return SPM_ERR_ARG;
+  std::lock_guard<std::mutex> lk(e->mu);
+  e->model.unk_surface.assign(surface ? surface : "", bytes);
+  e->dec_ready = false;
+  return SPM_OK;
+}
+
+int spm_decode_ids(spm_engine *e, const int32_t *ids, const uint64_t *id_offsets, size_t n, const char **text,
+                   const uint64_t **text_offsets) {
+  if (!e || !id_offsets || !text || !text_offsets) return SPM_ERR_ARG;
+  std::lock_guard<std::mutex> lk(e->mu);
+  auto set_error = [&](const std::string &m) { e->set_error(m); };
+  if (n >= 0xFFFFFFF0ull) { set_error("too many id lists in one call"); return SPM_ERR_ARG; }
+  for (size_t i = 0; i < n; ++i)
+    if (id_offsets[i + 1] < id_offsets[i]) { set_error("id_offsets must be non-decreasing"); return SPM_ERR_ARG; }
+  const uint64_t base = id_offsets[0];
+  const uint64_t total_ids = id_offsets[n] - base;
+  if (total_ids && !ids) return SPM_ERR_ARG;
+  if (!e->model.denormalizer_charsmap.empty()) {
+    set_error("Decode: models with a denormalizer_spec are not on the device path");
+    return SPM_ERR_UNSUPPORTED;
+  }
+  CUDA_TRY(cudaSetDevice(e->device));
+  { const int rc = e->ensure_decode_tables(); if (rc) return rc; }
+  cudaStream_t st = e->stream;
+  e->last_launches = 0;
+  CUDA_TRY(e->h_dec_text_offsets.ensure(n + 1));
+  if (n == 0) {
+    CUDA_TRY(e->h_dec_text.ensure(1));
+    e->h_dec_text_offsets.p[0] = 0;
+    *text = e->h_dec_text.p;
+    *text_offsets = e->h_dec_text_offsets.p;
+    return SPM_OK;
+  }
+  CUDA_TRY(e->d_dec_ids.ensure(total_ids + 1));
+  CUDA_TRY(e->d_offsets.ensure(n + 1));
+  CUDA_TRY(e->d_sent_start.ensure(n));
+  CUDA_TRY(e->d_sent_count.ensure(n));
+  CUDA_TRY(e->d_ctrl32.ensure(16));
+  CUDA_TRY(e->d_ctrl64.ensure(8));
+  CUDA_TRY(e->h_ctrl32.ensure(16));
+  CUDA_TRY(e->h_ctrl64.ensure(8));
+  CUDA_TRY(e->d_dec_text_offsets.ensure(n + 1));
+  if (total_ids) CUDA_TRY(cudaMemcpyAsync(e->d_dec_ids.p, ids + base, total_ids * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(e->d_offsets.p, id_offsets, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+  e->last_h2d = total_ids * sizeof(int32_t) + (n + 1) * sizeof(uint64_t);
+  const uint32_t n32 = static_cast<uint32_t>(n);
+  unsigned long long tmp_cap = total_ids * 6 + 16ull * n + (1u << 20);  // retried with the exact size on overflow
+  unsigned long long tot = 0;
+  for (int attempt = 0; attempt < 3; ++attempt) {
+    CUDA_TRY(e->d_dec_tmp.ensure(tmp_cap));
+    CUDA_TRY(cudaMemsetAsync(e->d_ctrl32.p, 0, 16 * sizeof(uint32_t), st));
+    CUDA_TRY(cudaMemsetAsync(e->d_ctrl64.p, 0, 8 * sizeof(unsigned long long), st));
+    KDecode D{};
+    D.ids = e->d_dec_ids.p - base;
+    D.id_offsets = reinterpret_cast<const unsigned long long *>(e->d_offsets.p);
+    D.n = n32;
+    D.vocab = e->model.vocab_size();
+    D.dec_off = e->d_dec_off.p;
+    D.dec_bytes = e->d_dec_bytes.p;
+    D.dec_info = e->d_dec_info.p;
+    D.strip = (e->model.add_dummy_prefix || e->model.remove_extra_whitespaces) ? 1u : 0u;
+    D.rm = e->model.remove_extra_whitespaces ? 1u : 0u;
+    D.tmp = e->d_dec_tmp.p;
+    D.tmp_cap = tmp_cap;
+    D.cursor = e->d_ctrl64.p;
+    D.sent_start = e->d_sent_start.p;
+    D.sent_count = e->d_sent_count.p;
+    D.status = e->d_ctrl32.p;
+    CUDA_TRY(cudaEventRecord(e->ev[0], st));
+    const int grid = static_cast<int>(std::min<size_t>(static_cast<size_t>(e->sm_count) * 8, (n + 7) / 8));
+    decode_warp_kernel<<<grid, 256, 0, st>>>(D);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(e->ev[1], st));
+    ++e->last_launches;
+    CUDA_TRY(cudaMemcpyAsync(e->h_ctrl32.p, e->d_ctrl32.p, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(e->h_ctrl64.p, e->d_ctrl64.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (e->h_ctrl32.p[1] == 2u) {  // :915-918
+      set_error("Invalid id: " + std::to_string(static_cast<int32_t>(e->h_ctrl32.p[3])));
+      return SPM_ERR_ARG;
+    }
+    if (e->h_ctrl32.p[1] == 1u) {
+      set_error("Decode: byte piece of id " + std::to_string(e->h_ctrl32.p[3]) + " is not of the form <0xXX>");
+      return SPM_ERR_ENCODE;
+    }
+    tot = e->h_ctrl64.p[0];
+    if (e->h_ctrl32.p[2]) { tmp_cap = tot + 1024; continue; }
+    break;
+  }
+  if (e->h_ctrl32.p[2]) { set_error("Decode: temporary buffer overflow persisted"); return SPM_ERR_CAPACITY; }
+  // offsets (exclusive scan) + gather into list order: the kernels of the encode path
+  const uint32_t nb = (n32 + kScanChunk - 1) / kScanChunk;
+  CUDA_TRY(e->d_block_sums.ensure(nb + 1));
+  CUDA_TRY(e->d_dec_text.ensure(tot + 16));
+  scan_block_sums_kernel<<<nb, 256, 0, st>>>(e->d_sent_count.p, n32, e->d_block_sums.p, 0);
+  scan_block_prefix_kernel<<<1, 1024, 0, st>>>(e->d_block_sums.p, nb, e->d_ctrl64.p + 2);
+  scan_write_gather_kernel<uint8_t><<<nb, 256, 0, st>>>(e->d_sent_count.p, n32, e->d_block_sums.p, e->d_dec_text_offsets.p,
+                                                        e->d_sent_start.p, e->d_dec_tmp.p, e->d_dec_text.p, nullptr, nullptr,
+                                                        e->d_dec_text.cap, 0, 0ull);
+  CUDA_TRY(cudaGetLastError());
+  e->last_launches += 3;
+  CUDA_TRY(cudaEventRecord(e->ev[2], st));
+  CUDA_TRY(e->h_dec_text.ensure(tot + 1));
+  if (tot) CUDA_TRY(cudaMemcpyAsync(e->h_dec_text.p, e->d_dec_text.p, tot, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(e->h_dec_text_offsets.p, e->d_dec_text_offsets.p, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  e->last_d2h = tot + (n + 1) * sizeof(uint64_t);
+  finish_timing(e);
+  e->h_dec_text.p[tot] = 0;
+  *text = e->h_dec_text.p;
+  *text_offsets = e->h_dec_text_offsets.p;
+  return SPM_OK;
 }
 
 void *spm_host_alloc(size_t bytes) {

@@ -79,6 +79,7 @@ bool ParseModelProto(const void *data, size_t len, ModelData *m, std::string *er
         if (f2 == 3 && w2 == 0) m->model_type = static_cast<int32_t>(v2);
         else if (f2 == 35 && w2 == 0) m->byte_fallback = v2 != 0;
         else if (f2 == 24 && w2 == 0) m->treat_whitespace_as_suffix = v2 != 0;
+        else if (f2 == 44 && w2 == 2) m->unk_surface = s2.str();
         else if (f2 == 45 && w2 == 2) m->unk_piece = s2.str();
         else if (f2 == 46 && w2 == 2) m->bos_piece = s2.str();
         else if (f2 == 47 && w2 == 2) m->eos_piece = s2.str();
@@ -92,6 +93,12 @@ bool ParseModelProto(const void *data, size_t len, ModelData *m, std::string *er
         else if (f2 == 3 && w2 == 0) m->add_dummy_prefix = v2 != 0;
         else if (f2 == 4 && w2 == 0) m->remove_extra_whitespaces = v2 != 0;
         else if (f2 == 5 && w2 == 0) m->escape_whitespaces = v2 != 0;
+      }
+    } else if (fno == 5) {  // denormalizer_spec (a NormalizerSpec)
+      uint32_t f2, w2; uint64_t v2; Cursor s2{nullptr, nullptr};
+      while (!s.done()) {
+        if (!s.field(&f2, &w2, &v2, &s2)) { *err = "malformed denormalizer_spec"; return false; }
+        if (f2 == 2 && w2 == 2) m->denormalizer_charsmap = s2.str();
       }
     } else if (fno == 4) {  // SelfTestData
       uint32_t f2, w2; uint64_t v2; Cursor s2{nullptr, nullptr};

@@ -28,6 +28,8 @@ struct ModelData {
   bool escape_whitespaces = true;           // NormalizerSpec :263
   std::string charsmap;                     // NormalizerSpec.precompiled_charsmap :252
   std::string unk_piece = "<unk>", bos_piece = "<s>", eos_piece = "</s>", pad_piece = "<pad>";  // :220-223
+  std::string unk_surface = " \xE2\x81\x87 ";  // TrainerSpec :228 (Decode)
+  std::string denormalizer_charsmap;           // ModelProto.denormalizer_spec :327 (Decode; not supported on the device)
   std::vector<std::pair<std::string, std::string>> self_test;  // SelfTestData :277-283
 
   int vocab_size() const { return static_cast<int>(scores.size()); }

@@ -93,6 +93,19 @@ class Engine:
         n2o = np.ctypeslib.as_array(ctypes.cast(p[5], ctypes.POINTER(ctypes.c_uint32)), (tn + n,)).copy()
         return dict(ids=ids, tok_end=te, id_offsets=ido, normalized=norm, norm_offsets=no, n2o=n2o)
 
+    def decode_packed(self, ids, id_offsets):
+        """Batch Decode of packed id lists -> (text uint8[], text_offsets uint64[n+1])."""
+        n = len(id_offsets) - 1
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        ido = np.ascontiguousarray(id_offsets, dtype=np.uint64)
+        text = ctypes.c_void_p()
+        to = ctypes.c_void_p()
+        self._check(self._lib.spm_decode_ids(self._h, ids.ctypes.data, ido.ctypes.data, n, ctypes.byref(text), ctypes.byref(to)))
+        o = np.ctypeslib.as_array(ctypes.cast(to, ctypes.POINTER(ctypes.c_uint64)), (n + 1,)).copy()
+        tot = int(o[n])
+        t = np.frombuffer(ctypes.string_at(text, tot), dtype=np.uint8) if tot else np.zeros(0, np.uint8)
+        return t, o
+
     def set_random_seed(self, seed):
         self._check(self._lib.spm_set_random_seed(self._h, seed))
 
@@ -161,6 +174,20 @@ class SentencePieceProcessor:
             raise RuntimeError("Model is not initialized.")  # sentencepiece_processor.cc:293-299
 
     # sentencepiece_processor.h:458 + python batch entry sentencepiece.i:439-446
+    def DecodeIds(self, input):
+        """Decode(ids) (src/sentencepiece_processor.h, python __init__.py DecodeIds): one id list or a list of lists."""
+        self._require()
+        single = len(input) == 0 or not isinstance(input[0], (list, tuple, np.ndarray))
+        lists = [input] if single else list(input)
+        ido = np.zeros(len(lists) + 1, dtype=np.uint64)
+        if lists:
+            ido[1:] = np.cumsum([len(x) for x in lists], dtype=np.uint64)
+        ids = np.concatenate([np.asarray(x, dtype=np.int32) for x in lists]) if int(ido[-1]) else np.zeros(0, np.int32)
+        text, to = self._engine.decode_packed(ids, ido)
+        raw = text.tobytes()
+        out = [raw[int(to[i]):int(to[i + 1])].decode("utf-8", errors="replace") for i in range(len(lists))]
+        return out[0] if single else out
+
     def EncodeAsIds(self, input):
         self._require()
         single = isinstance(input, (str, bytes))
