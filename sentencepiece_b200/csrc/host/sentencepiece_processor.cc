@@ -143,6 +143,42 @@ util::Status SentencePieceProcessor::EncodePacked(const char *bytes, const uint6
   return FromEngine(engine_, spm_encode_ids(engine_, bytes, offsets, n, ids, id_offsets));
 }
 
+util::Status SentencePieceProcessor::Decode(const std::vector<std::vector<int>> &ids,
+                                            std::vector<std::string> *detokenized) const {
+  if (!engine_) return status();
+  if (!detokenized) return Internal("output container is null");  // CHECK_OR_RETURN_STATUS_STL
+  detokenized->clear();
+  std::vector<int32_t> packed;
+  std::vector<uint64_t> offs(1, 0);
+  for (const auto &l : ids) {
+    packed.insert(packed.end(), l.begin(), l.end());
+    offs.push_back(packed.size());
+  }
+  const char *text = nullptr;
+  const uint64_t *to = nullptr;
+  const int rc = spm_decode_ids(engine_, packed.data(), offs.data(), ids.size(), &text, &to);
+  if (rc) return FromEngine(engine_, rc);
+  detokenized->reserve(ids.size());
+  for (size_t i = 0; i < ids.size(); ++i) detokenized->emplace_back(text + to[i], text + to[i + 1]);
+  return util::OkStatus();
+}
+
+util::Status SentencePieceProcessor::Decode(const std::vector<int> &ids, std::string *detokenized) const {
+  if (!engine_) return status();
+  if (!detokenized) return Internal("output container is null");
+  std::vector<std::string> out;
+  const util::Status st = Decode(std::vector<std::vector<int>>{ids}, &out);
+  if (!st.ok()) return st;
+  *detokenized = std::move(out[0]);
+  return util::OkStatus();
+}
+
+std::string SentencePieceProcessor::DecodeIds(const std::vector<int> &ids) const {
+  std::string out;
+  Decode(ids, &out);
+  return out;
+}
+
 namespace {
 void Pack(const std::vector<std::string_view> &in, std::string *bytes, std::vector<uint64_t> *offs) {
   size_t total = 0;

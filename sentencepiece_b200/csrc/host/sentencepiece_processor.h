@@ -76,6 +76,13 @@ class SentencePieceProcessor {
   util::Status EncodePacked(const char *bytes, const uint64_t *offsets, size_t n, const int32_t **ids,
                             const uint64_t **id_offsets) const;
 
+  // ---- Decode(ids) (src/sentencepiece_processor.h Decode(const std::vector<int>&, std::string*)); the batch form is
+  //      one device call for all lists.  An id outside [0, GetPieceSize()) fails the call like the reference's
+  //      kOutOfRange (sentencepiece_processor.cc:915-918); decode_extra_options are not applied. ----
+  util::Status Decode(const std::vector<int> &ids, std::string *detokenized) const;
+  util::Status Decode(const std::vector<std::vector<int>> &ids, std::vector<std::string> *detokenized) const;
+  std::string DecodeIds(const std::vector<int> &ids) const;
+
   // ---- vocabulary accessors used by callers of the encode path ----
   int GetPieceSize() const;
   int PieceToId(std::string_view piece) const;
