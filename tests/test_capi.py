@@ -41,3 +41,12 @@ def test_product_does_not_import_oracle():
                 txt = open(os.path.join(d, f), errors="replace").read()
                 assert "oracle/" not in txt.replace("see oracle/Makefile", "") and "import oracle" not in txt \
                     and "from oracle" not in txt, os.path.join(d, f)
+
+
+def test_makefile_tracks_every_kernel_header():
+    """The engine is one translation unit that includes every kernel header: the Makefile rule must depend on all of
+    them (a missing header dependency once made `make` a silent no-op for three kernel experiments)."""
+    csrc = os.path.join(ROOT, "sentencepiece_b200", "csrc")
+    mk = open(os.path.join(csrc, "Makefile")).read()
+    rule = re.search(r"^\$\(OUT\)/engine\.o:(.*)$", mk, re.M).group(1)
+    assert "$(wildcard *.cuh)" in rule and "$(wildcard *.h)" in rule
