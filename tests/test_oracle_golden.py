@@ -88,3 +88,30 @@ def test_live_reference_normalize_alignment(corpus_gen):
     om, rm = oracle_py.OracleModel(mb), oracle_py.RefModel(mb)
     for s in corpus_gen.lines("mixed", 779, 400):
         assert om.normalize(s) == rm.normalize(s)
+
+
+@pytest.mark.skipif(not oracle_py.ref_available(), reason="oracle/_ref is not built here")
+@pytest.mark.parametrize("model", ["uni32k", "mix_bf8k", "bpe32k", "mix_bpe4k"])
+def test_fuzz_oracle_vs_live_reference(model):
+    """Random mixes of ASCII, runs of spaces, CJK, emoji, NFKC compatibility forms, combining marks, control bytes,
+    NUL, reserved piece strings and malformed UTF-8: oracle ids (and the decoded text of those ids) == reference."""
+    rng = np.random.default_rng(20260922)
+    chunks = [b" ", b"  ", b"a", b"e", b"the", b"ing", "▁".encode(), "あ".encode(), "ガ".encode(), "ｗ".encode(),
+              "㍿".encode(), "😀".encode(), b"\xff", b"\xc0\xaf", b"\xed\xa0\x80", b"\xe2\x82", b"\x00", b"\t", b"\n",
+              "Å".encode(), b"1", "①".encode(), b".", b",", " ".encode(), "　".encode(), b"<unk>", b"<s>",
+              "�".encode()]
+    sents = []
+    for _ in range(6000):
+        parts = [chunks[int(rng.integers(0, len(chunks)))] for _ in range(int(rng.integers(0, 40)))]
+        if rng.random() < 0.2:
+            parts.append(bytes(rng.integers(0, 256, size=int(rng.integers(1, 12)), dtype=np.uint8)))
+        sents.append(b"".join(parts))
+    mb = model_bytes(model)
+    om, rm = oracle_py.OracleModel(mb), oracle_py.RefModel(mb)
+    buf, offs = oracle_py.pack(sents)
+    a, ao = om.encode_batch(buf, offs)
+    b, bo = rm.encode_batch(buf, offs, threads=8)
+    assert np.array_equal(ao, bo) and np.array_equal(a, b)
+    t1, o1 = om.decode_batch(b, bo)
+    t2, o2 = rm.decode_batch(b, bo, threads=8)
+    assert np.array_equal(o1, o2) and np.array_equal(t1, t2)
