@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(768, 1) encode_bpe_lane_kernel(const KModel M,
     if (have) {
       const unsigned long long off = B.offsets[sent];
       const unsigned long long len64 = B.offsets[sent + 1] - off;
-      if (len64 > 4ull * cap) defer = true;
+      if (len64 > 4ull * cap || off < B.off_lo || off + len64 > B.off_hi) defer = true;
       else {
         n = lane_normalize(M, B.bytes + off, static_cast<uint32_t>(len64), c, cap);
         if (n == 0xFFFFFFFFu) { defer = true; n = 0; }

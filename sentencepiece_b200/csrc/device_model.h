@@ -19,6 +19,7 @@ enum : uint32_t {
   kFlagHasCharsmap = 1u << 6,
   kFlagBpeWordSplit = 1u << 7,     // no piece has U+2581 past byte 0 (SURVEY 7 "exact decomposition")
   kFlagHasUnused = 1u << 8,        // some piece is currently UNUSED (SetVocabulary)
+  kFlagFastWords = 1u << 10,       // KModel::word_safe is valid (whole-word shortcut of the unigram lane kernel)
   kFlagRegularScores = 1u << 9,    // every piece score is 0 or has 2^-10 <= |score| <= 2^10 (exact float fold)
 };
 
@@ -54,6 +55,12 @@ struct KModel {
   const int32_t *byte_to_id;  // [256] PieceToId(ByteToPiece(b)), sentencepiece_processor.cc:587-588
   const float *scores;        // [vocab] (BPE: score of a piece id)
   const uint8_t *types;       // [vocab] live piece types
+  // [trie_units] whole-word shortcut (lane_kernel.cuh): a word that is exactly the piece at this unit and ends at a normalized
+  // byte position <= word_safe[unit] is certain to be encoded as that piece alone (0 = never); see engine.cu
+  const uint16_t *word_safe;
+  // [trie_units] BPE lane2 kernel: vocab id of the piece at this unit when a word that is exactly the piece encodes
+  // to that single id (its merge sequence reproduces it), else 0xFFFFFFFF
+  const uint32_t *word_fast;
   int32_t unk_id;
   float unk_score;  // min_score_ - kUnkPenalty, unigram_model.cc:955
   float max_score;  // unigram_model.cc:658-663 (FLT_MIN quirk)
@@ -66,6 +73,10 @@ struct KBatch {
   const uint8_t *bytes;
   const uint64_t *offsets;  // [n+1]
   uint32_t n;
+  // sentences whose [offset, offset + length) does not lie inside [off_lo, off_hi] are not touched by the lane
+  // kernels (deferred; the host validates the offsets and reports the error): a batch with broken offsets must
+  // not make the kernel read outside the batch's buffer
+  unsigned long long off_lo, off_hi;
   const uint32_t *order;    // lane kernels: processing order (a permutation of 0..n-1), or null = input order
   // streamed host batches: *ready = sentences of the whole batch whose bytes have arrived (input order);
   // this launch covers sentences ready_base .. ready_base + n, which arrive in pieces of 2^piece_shift

@@ -28,6 +28,7 @@
 #include "../../include/spm_b200.h"
 #include "bpe_kernel.cuh"
 #include "bpe_lane_kernel.cuh"
+#include "bpe_lane2_kernel.cuh"
 #include "device_model.h"
 #include "kernels.cuh"
 #include "lane_kernel.cuh"
@@ -140,6 +141,11 @@ struct spm_engine {
   DevBuf<int32_t> d_id, d_cm_solo, d_byte_to_id;
   DevBuf<uint8_t> d_cm_targets, d_types;
   DevBuf<float> d_scores;
+  DevBuf<uint16_t> d_word_safe;
+  DevBuf<uint32_t> d_word_fast;
+  int bpe_lane_version = 2;  // SPM_B200_BPE_LANE_V
+  bool fast_words = true;  // SPM_B200_FASTWORDS
+  int upload_word_safe();
   KModel km{};
 
   // tuning
@@ -174,6 +180,7 @@ struct spm_engine {
   bool sort_by_length = true;
   // streamed host batches (encode_host_streamed): set around run_device calls
   const uint32_t *cur_ready = nullptr;
+  unsigned long long cur_off_lo = 0, cur_off_hi = ~0ull;  // valid offset range of the batch run_device is given
   uint32_t cur_ready_base = 0, cur_piece_shift = 0;
   DevBuf<uint8_t> s_bytes;
   DevBuf<uint64_t> s_offsets;
@@ -189,13 +196,43 @@ struct spm_engine {
   int fused_skip = 0, fused_backoff = 8;
   DevBuf<uint32_t> d_seg_done, d_sent_rel;
   DevBuf<unsigned long long> d_seg_words;
-  // the conditions under which run_device takes a lane kernel for an ids-only batch
-  bool uses_lane_kernel() const {
-    if (G != 1) return false;
-    if (model.model_type == SPM_BPE)
-      return (km.flags & kFlagBpeWordSplit) && (km.flags & kFlagEscapeWs) && !(km.flags & (kFlagHasUserSymbols | kFlagHasUnused));
-    return trie.max_key_len <= 62;
+  // Launch geometry of the lane kernels for an ids-only batch; ok == false: the model / tuning is outside the lane
+  // kernels (the tile, warp or general BPE kernels take the batch).  Shared memory per warp grows with the longest
+  // piece (ring of max piece length + 2 slots), so the warps per CTA shrink until the rings fit.
+  struct LaneGeom {
+    bool ok = false;
+    int version = 1;       // BPE: 1 = encode_bpe_lane_kernel (sentence per lane), 2 = encode_bpe_lane2_kernel (word lists)
+    int threads = 0;
+    uint32_t R = 0, smem = 0;
+  };
+  bool any_user_defined = false;
+  LaneGeom lane_geometry() const {
+    LaneGeom g;
+    if (G != 1) return g;
+    const size_t avail = smem_optin > kLaneTableBytes ? smem_optin - kLaneTableBytes : 0;
+    if (model.model_type == SPM_BPE) {
+      if (!((km.flags & kFlagBpeWordSplit) && (km.flags & kFlagEscapeWs) && !(km.flags & (kFlagHasUserSymbols | kFlagHasUnused))))
+        return g;
+      g.version = bpe_lane_version == 2 ? 2 : 1;
+      const size_t per_warp = g.version == 2 ? kBpeLane2WarpBytes : kBpeLaneWarpBytes;
+      const int warps = static_cast<int>(std::min<size_t>(std::min(threads, 768) / 32, avail / per_warp));
+      if (warps < 4) return g;
+      g.ok = true;
+      g.threads = warps * 32;
+      g.smem = static_cast<uint32_t>(kLaneTableBytes + static_cast<size_t>(warps) * per_warp);
+      return g;
+    }
+    if (trie.max_key_len > 62) return g;
+    g.R = trie.max_key_len + 2;
+    const size_t ring = lane_ring_bytes(g.R);
+    const int warps = static_cast<int>(std::min<size_t>(threads / 32, avail / ring));
+    if (warps < 4) return g;
+    g.ok = true;
+    g.threads = warps * 32;
+    g.smem = static_cast<uint32_t>(kLaneTableBytes + static_cast<size_t>(warps) * ring);
+    return g;
   }
+  bool uses_lane_kernel() const { return lane_geometry().ok; }
   // Decode (K7): per-id decoded strings, built on first use
   DevBuf<uint32_t> d_dec_off, d_dec_info;
   DevBuf<uint8_t> d_dec_bytes, d_dec_tmp, d_dec_text;
@@ -435,8 +472,11 @@ int spm_engine::build_tables() {
              (m.escape_whitespaces ? kFlagEscapeWs : 0) | (m.treat_whitespace_as_suffix ? kFlagWsSuffix : 0) |
              (m.byte_fallback ? kFlagByteFallback : 0) | (!user_trie.link.empty() ? kFlagHasUserSymbols : 0) |
              (charsmap_units ? kFlagHasCharsmap : 0) | (bpe_word_split ? kFlagBpeWordSplit : 0);
-  for (uint8_t t : m.types)
+  any_user_defined = false;
+  for (uint8_t t : m.types) {
     if (t == SPM_UNUSED) km.flags |= kFlagHasUnused;
+    if (t == SPM_USER_DEFINED) any_user_defined = true;
+  }
   {
     bool regular = true;
     for (const TrieKey &k : keys) {
@@ -445,6 +485,133 @@ int spm_engine::build_tables() {
     }
     if (regular) km.flags |= kFlagRegularScores;
   }
+  return upload_word_safe();
+}
+
+// whole-word shortcut of the unigram lane kernel (lane_kernel.cuh): for every NORMAL piece P, seen as a word of its own, the largest
+// normalized end position e up to which EncodeOptimized (unigram_model.cc:889-1020) is CERTAIN to encode the word
+// as P alone, whatever precedes it.
+//
+// Setting: no piece contains U+2581 past byte 0 and whitespace is escaped, so a word [b, e) -- U+2581 (or the text
+// start) up to the next U+2581 -- is only entered through position b and only left through e: the recurrence inside
+// the word depends on the rest of the sentence through B = best_path_score[b] alone.  Let S_P be P's score and
+// S_alt the best exact (real-number) score of any OTHER segmentation of the word into pieces / UNK edges, built
+// with the reference's edge rules (has_single_node, UNUSED skipped, unk_score = min_score - 10).  The reference
+// relaxes the whole-word edge first (start b is the earliest start of any edge into e), storing fl(S_P + B).  Every
+// float it stores for a position inside the word is within (characters so far) roundings of B + (exact best), and
+// every rounding is at most ulp(Vmax) with Vmax >= any |partial score| <= e * maxabs (at most one edge per byte,
+// each of magnitude <= maxabs).  So a later candidate into e is at most B + S_alt + c * ulp(Vmax) and cannot
+// exceed the stored value (>= B + S_P - ulp(Vmax)) when  S_P - S_alt > (c + 1) * ulp(Vmax).  The table stores the
+// largest e for which that holds with a further factor of two of slack on both the margin and Vmax.
+int spm_engine::upload_word_safe() {
+  std::vector<uint16_t> safe(trie.link.size(), 0);
+  const bool eligible = fast_words && model.model_type == SPM_UNIGRAM && bpe_word_split && model.escape_whitespaces &&
+                        !model.treat_whitespace_as_suffix && !any_user_defined && trie.max_key_len <= 62;
+  km.flags &= ~kFlagFastWords;
+  if (eligible) {
+    const int V = model.vocab_size();
+    const double unk = static_cast<double>(min_score - 10.0f);
+    double maxabs = std::fabs(unk);
+    for (int i = 0; i < V; ++i)
+      if (model.types[i] == SPM_NORMAL) maxabs = std::max(maxabs, static_cast<double>(std::fabs(model.scores[i])));
+    maxabs = std::max(maxabs, 1e-3);
+    const double kNegInf = -1e300;
+    std::vector<double> E;
+    for (int i = 0; i < V; ++i) {
+      if (model.types[i] != SPM_NORMAL) continue;
+      const uint32_t unit = trie.unit_of_id[i];
+      if (unit == 0xFFFFFFFFu) continue;
+      const unsigned char *p = reinterpret_cast<const unsigned char *>(model.piece(i));
+      const uint32_t L = static_cast<uint32_t>(model.piece_len(i));
+      E.assign(L + 1, kNegInf);
+      E[0] = 0.0;
+      uint32_t chars = 0;
+      for (uint32_t st = 0; st < L;) {
+        static const uint8_t kLen[16] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 2, 2, 3, 4};  // OneCharLen, util.h:151-153
+        const uint32_t mb = std::min<uint32_t>(kLen[p[st] >> 4], L - st);
+        ++chars;
+        if (E[st] > kNegInf) {
+          bool has_single = false;
+          uint32_t l = trie.link[0];
+          for (uint32_t k = st; k < L; ++k) {
+            const uint32_t v = (l >> kLinkBaseShift) ^ p[k];
+            if (v >= trie.link.size() || (trie.link[v] & kLinkLabelMask) != p[k]) break;
+            l = trie.link[v];
+            const uint32_t kind = (l >> kLinkKindShift) & 3u;
+            if (kind != kKindNormal && kind != kKindUserDefined) continue;
+            const uint32_t len = k + 1 - st;
+            if (len == mb) has_single = true;
+            if (st == 0 && len == L) continue;  // the whole-word edge itself
+            float sc;
+            memcpy(&sc, &trie.val[v], 4);
+            E[st + len] = std::max(E[st + len], E[st] + static_cast<double>(sc));
+          }
+          if (!has_single) E[st + mb] = std::max(E[st + mb], E[st] + unk);
+        }
+        st += mb;
+      }
+      const double margin = E[L] > kNegInf ? static_cast<double>(model.scores[i]) - E[L] : 1e300;
+      if (!(margin > 0.0)) continue;
+      // (chars + 1) * 2^(kk - 23) < margin / 2   with   Vmax < 2^(kk + 1)
+      const double x = margin / (2.0 * (chars + 1));
+      const int kk = std::min(40, std::ilogb(x) + 22);
+      if (kk < -40) continue;
+      const double vmax = std::ldexp(1.0, kk + 1) / (2.0 * maxabs);  // largest admissible e (Vmax = e * maxabs, 2x slack)
+      const double e_max = std::floor(vmax) - 1.0;
+      if (e_max >= L) safe[unit] = static_cast<uint16_t>(std::min(65535.0, e_max));
+    }
+    km.flags |= kFlagFastWords;
+  }
+  // BPE (bpe_lane2_kernel.cuh): word_fast[unit] = id of the piece when the reference's merge loop
+  // (bpe_model.cc:38-203: best score, leftmost on ties; candidates are string members of pieces_) run on the piece's
+  // own characters ends with the piece as its only symbol; such a word needs no merge loop on the device.
+  std::vector<uint32_t> fastw(trie.link.size(), 0xFFFFFFFFu);
+  if (model.model_type == SPM_BPE && bpe_word_split && model.escape_whitespaces && !any_user_defined &&
+      !(km.flags & kFlagHasUnused)) {
+    static const uint8_t kLen[16] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 2, 2, 3, 4};
+    auto find = [&](const unsigned char *p, uint32_t len) -> uint32_t {  // exact match: unit of the piece, or ~0
+      uint32_t l = trie.link[0], v = 0xFFFFFFFFu;
+      for (uint32_t k = 0; k < len; ++k) {
+        v = (l >> kLinkBaseShift) ^ p[k];
+        if (v >= trie.link.size() || (trie.link[v] & kLinkLabelMask) != p[k]) return 0xFFFFFFFFu;
+        l = trie.link[v];
+      }
+      return ((l >> kLinkKindShift) & 3u) != kKindNone ? v : 0xFFFFFFFFu;
+    };
+    std::vector<std::pair<uint32_t, uint32_t>> sy;  // (start, length) of the live symbols
+    for (int i = 0; i < model.vocab_size(); ++i) {
+      const uint32_t unit = trie.unit_of_id[i];
+      if (unit == 0xFFFFFFFFu) continue;
+      const unsigned char *p = reinterpret_cast<const unsigned char *>(model.piece(i));
+      const uint32_t L = static_cast<uint32_t>(model.piece_len(i));
+      sy.clear();
+      for (uint32_t st = 0; st < L;) {
+        const uint32_t mb = std::min<uint32_t>(kLen[p[st] >> 4], L - st);
+        sy.emplace_back(st, mb);
+        st += mb;
+      }
+      while (sy.size() > 1) {
+        int bi = -1;
+        float best = 0.f;
+        for (size_t j = 0; j + 1 < sy.size(); ++j) {
+          const uint32_t u = find(p + sy[j].first, sy[j].second + sy[j + 1].second);
+          if (u == 0xFFFFFFFFu) continue;
+          float sc;
+          memcpy(&sc, &trie.val[u], 4);
+          if (bi < 0 || sc > best) { best = sc; bi = static_cast<int>(j); }
+        }
+        if (bi < 0) break;
+        sy[bi].second += sy[bi + 1].second;
+        sy.erase(sy.begin() + bi + 1);
+      }
+      if (sy.size() == 1) fastw[unit] = static_cast<uint32_t>(i);
+    }
+  }
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(d_word_safe.upload(safe));
+  CUDA_TRY(d_word_fast.upload(fastw));
+  km.word_safe = d_word_safe.p;
+  km.word_fast = d_word_fast.p;
   return SPM_OK;
 }
 
@@ -467,12 +634,14 @@ int spm_engine::upload_types() {
     trie.link[u] = (trie.link[u] & ~(3u << kLinkKindShift)) | (kind << kLinkKindShift);
   }
   bool any_unused = false;
-  for (uint8_t t : model.types) any_unused |= t == SPM_UNUSED;
+  any_user_defined = false;
+  for (uint8_t t : model.types) { any_unused |= t == SPM_UNUSED; any_user_defined |= t == SPM_USER_DEFINED; }
   km.flags = (km.flags & ~kFlagHasUnused) | (any_unused ? kFlagHasUnused : 0u);
   CUDA_TRY(cudaSetDevice(device));
   CUDA_TRY(d_link.upload(trie.link));
   CUDA_TRY(d_types.upload(model.types));
-  return upload_node2();
+  { const int rc = upload_node2(); if (rc) return rc; }
+  return upload_word_safe();
 }
 
 // -------------------------------------------------------------- launches ---
@@ -522,6 +691,7 @@ int spm_engine::configure_kernel_attrs() {
   CUDA_TRY(set_smem(encode_unigram_long_kernel<true>, mx));
   CUDA_TRY(set_smem(encode_unigram_lane_kernel, mx));
   CUDA_TRY(set_smem(encode_bpe_lane_kernel, mx));
+  CUDA_TRY(set_smem(encode_bpe_lane2_kernel, mx));
   CUDA_TRY(set_smem(nbest_lane_kernel<kNbestTop, 1024>, mx));
   CUDA_TRY(set_smem(encode_unigram_warp_kernel<512>, mx));
   CUDA_TRY(set_smem(encode_unigram_warp_kernel<1024>, mx));
@@ -569,13 +739,12 @@ int spm_engine::run_device(const uint8_t *d_bytes_base, const uint64_t *d_offs, 
   const int tile_threads = std::min(threads, 512);
   const uint32_t K = km.match_slots;
   LaunchGeom geom = plan_geometry(*this, spans, useG, tile_threads, ncap, K);
-  // fast unigram path: warp per sentence, register-resident Viterbi window
-  const bool lane_path = !bpe && !spans && trie.max_key_len <= 62 && G == 1;
-  const bool bpe_lane_path = bpe && !spans && G == 1 && (km.flags & kFlagBpeWordSplit) && (km.flags & kFlagEscapeWs) &&
-                             !(km.flags & (kFlagHasUserSymbols | kFlagHasUnused));
+  // fast paths: sentence per lane (lane kernels), or warp per sentence with a register-resident Viterbi window
+  const LaneGeom lg = spans ? LaneGeom{} : lane_geometry();
+  const bool lane_path = !bpe && lg.ok;
+  const bool bpe_lane_path = bpe && lg.ok;
   const bool warp_path = !bpe && !spans && trie.max_key_len <= 32 && G == 32;
   const int launch_threads = warp_path ? threads : tile_threads;
-  const uint32_t laneR = trie.max_key_len + 2;  // ring slots: positions [s, s + max piece length]
   if (bpe || warp_path) {
     // these kernels own a warp per sentence and their own scratch layout
     geom.tiles = launch_threads / 32;
@@ -587,20 +756,11 @@ int spm_engine::run_device(const uint8_t *d_bytes_base, const uint64_t *d_offs, 
     geom.smem_bytes = static_cast<uint32_t>(16 + static_cast<size_t>(geom.hot_link + geom.hot_val) * 4 +
                                             static_cast<size_t>(geom.tiles) * geom.tile_bytes);
   }
-  const int bpe_lane_threads = std::min(threads, 768);
-  if (bpe_lane_path) {
-    geom.tiles = bpe_lane_threads / 32;
-    geom.tile_bytes = kBpeLaneWarpBytes;
-    geom.hot_link = geom.hot_val = 0;
-    geom.smem_bytes = static_cast<uint32_t>(kLaneTableBytes + static_cast<size_t>(geom.tiles) * geom.tile_bytes);
-    const size_t warps_total = static_cast<size_t>(sm_count) * ctas_per_sm * geom.tiles;
-    CUDA_TRY(d_lane_slabs.ensure(warps_total * lane_slab_bytes(lane_cap) + 256));
-  }
-  if (lane_path) {
-    geom.tiles = threads / 32;
-    geom.tile_bytes = laneR * 32 * 8;
-    geom.hot_link = geom.hot_val = 0;  // the lane kernel reads the trie through L1: rings get the shared memory
-    geom.smem_bytes = static_cast<uint32_t>(kLaneTableBytes + static_cast<size_t>(geom.tiles) * geom.tile_bytes);
+  if (lane_path || bpe_lane_path) {
+    geom.tiles = lg.threads / 32;
+    geom.tile_bytes = bpe ? (lg.version == 2 ? kBpeLane2WarpBytes : kBpeLaneWarpBytes) : lane_ring_bytes(lg.R);
+    geom.hot_link = geom.hot_val = 0;  // the lane kernels read the trie through L1: rings / word arrays get the shared memory
+    geom.smem_bytes = lg.smem;
     const size_t warps_total = static_cast<size_t>(sm_count) * ctas_per_sm * geom.tiles;
     CUDA_TRY(d_lane_slabs.ensure(warps_total * lane_slab_bytes(lane_cap) + 256));
   }
@@ -640,6 +800,8 @@ int spm_engine::run_device(const uint8_t *d_bytes_base, const uint64_t *d_offs, 
     B.bytes = d_bytes_base;
     B.offsets = d_offs;
     B.n = n32;
+    B.off_lo = cur_off_lo;
+    B.off_hi = cur_off_hi;
     B.tmp_ids = d_tmp_ids.p;
     B.tmp_tok_end = d_tmp_tok_end.p;
     B.tmp_cap = tmp_cap;
@@ -667,13 +829,15 @@ int spm_engine::run_device(const uint8_t *d_bytes_base, const uint64_t *d_offs, 
       B.ready_base = cur_ready_base;
       B.piece_shift = cur_piece_shift;
     }
-    if (bpe_lane_path) {
-      encode_bpe_lane_kernel<<<grid, bpe_lane_threads, geom.smem_bytes, st>>>(M, B, d_lane_slabs.p, lane_cap);
+    if (bpe_lane_path && lg.version == 2) {
+      encode_bpe_lane2_kernel<<<grid, lg.threads, geom.smem_bytes, st>>>(M, B, d_lane_slabs.p, lane_cap);
+    } else if (bpe_lane_path) {
+      encode_bpe_lane_kernel<<<grid, lg.threads, geom.smem_bytes, st>>>(M, B, d_lane_slabs.p, lane_cap);
     } else if (bpe) {
       if (spans) encode_bpe_kernel<true><<<grid, tile_threads, geom.smem_bytes, st>>>(M, B);
       else encode_bpe_kernel<false><<<grid, tile_threads, geom.smem_bytes, st>>>(M, B);
     } else if (lane_path) {
-      encode_unigram_lane_kernel<<<grid, threads, geom.smem_bytes, st>>>(M, B, d_lane_slabs.p, lane_cap, laneR);
+      encode_unigram_lane_kernel<<<grid, lg.threads, geom.smem_bytes, st>>>(M, B, d_lane_slabs.p, lane_cap, lg.R);
     } else if (warp_path) {
       if (threads <= 512) encode_unigram_warp_kernel<512><<<grid, threads, geom.smem_bytes, st>>>(M, B);
       else encode_unigram_warp_kernel<1024><<<grid, threads, geom.smem_bytes, st>>>(M, B);
@@ -872,7 +1036,8 @@ int spm_engine::encode_host_pipelined(const char *bytes, const uint64_t *offsets
   // one group, so smaller chunks would only add idle warps (measured: 8 x 131k chunks cost 9.2 ms of
   // kernels against 6.5 ms for one launch)
   const bool is_bpe = model.model_type == SPM_BPE;
-  const size_t warps = static_cast<size_t>(sm_count) * ctas_per_sm * ((is_bpe ? std::min(threads, 768) : threads) / 32);
+  const LaneGeom lgw = lane_geometry();
+  const size_t warps = static_cast<size_t>(sm_count) * ctas_per_sm * ((lgw.ok ? lgw.threads : std::min(threads, 512)) / 32);
   size_t groups_per_warp = is_bpe ? 2 : 1;
   if (const char *v = getenv("SPM_B200_CHUNK_GROUPS")) groups_per_warp = std::max(1, atoi(v));
   const bool trace = getenv("SPM_B200_TRACE") != nullptr;
@@ -981,7 +1146,8 @@ int spm_engine::encode_host_streamed(const char *bytes, const uint64_t *offsets,
   constexpr size_t kPiece = size_t{1} << kPieceShift;
   const size_t P = (n + kPiece - 1) / kPiece;
   const bool is_bpe = model.model_type == SPM_BPE;
-  const size_t warps = static_cast<size_t>(sm_count) * ctas_per_sm * ((is_bpe ? std::min(threads, 768) : threads) / 32);
+  const LaneGeom lgw = lane_geometry();
+  const size_t warps = static_cast<size_t>(sm_count) * ctas_per_sm * ((lgw.ok ? lgw.threads : std::min(threads, 512)) / 32);
   size_t groups_per_warp = is_bpe ? 4 : 2;
   if (const char *v = getenv("SPM_B200_CHUNK_GROUPS")) groups_per_warp = std::max(1, atoi(v));
   const size_t min_chunk = std::max<size_t>(kPiece, warps * 32 * groups_per_warp);
@@ -1138,11 +1304,10 @@ int spm_engine::encode_host_fused(const char *bytes, const uint64_t *offsets, si
   CUDA_TRY(h_progress.ensure(8));
   *reinterpret_cast<volatile unsigned long long *>(h_progress.p) = 0;
   // ---- launch geometry of the lane kernels (as in run_device) ----
-  const int lane_threads = bpe ? std::min(threads, 768) : threads;
-  const uint32_t laneR = trie.max_key_len + 2;
-  const uint32_t smem = static_cast<uint32_t>(kLaneTableBytes + static_cast<size_t>(lane_threads / 32) *
-                                                                    (bpe ? kBpeLaneWarpBytes : laneR * 32 * 8));
-  if (smem > smem_optin) { set_error("shared-memory geometry does not fit"); return SPM_ERR_ARG; }
+  const LaneGeom lg = lane_geometry();
+  if (!lg.ok) { set_error("fused path: the model is outside the lane kernels"); return SPM_ERR_ARG; }
+  const int lane_threads = lg.threads;
+  const uint32_t smem = lg.smem;
   const int grid = sm_count * ctas_per_sm;
   CUDA_TRY(d_lane_slabs.ensure(static_cast<size_t>(grid) * (lane_threads / 32) * lane_slab_bytes(lane_cap) + 256));
   // ---- queue the whole input ----
@@ -1184,6 +1349,8 @@ int spm_engine::encode_host_fused(const char *bytes, const uint64_t *offsets, si
   B.bytes = s_bytes.p - offsets[0];
   B.offsets = s_offsets.p;
   B.n = n32;
+  B.off_lo = offsets[0];
+  B.off_hi = offsets[n];
   B.tmp_ids = d_tmp_ids.p;
   B.tmp_cap = tmp_cap;
   B.cursor = d_ctrl64.p;
@@ -1216,8 +1383,9 @@ int spm_engine::encode_host_fused(const char *bytes, const uint64_t *offsets, si
   CUDA_TRY(cudaEventRecord(ev[0], st));
   { const int rc = build_order(s_offsets.p, n, st, &B.order, 1u << kSegShift); if (rc) return rc; }
   if (!B.order) { set_error("fused path needs the segment order"); return SPM_ERR_ARG; }
-  if (bpe) encode_bpe_lane_kernel<<<grid, lane_threads, smem, st>>>(M, B, d_lane_slabs.p, lane_cap);
-  else encode_unigram_lane_kernel<<<grid, lane_threads, smem, st>>>(M, B, d_lane_slabs.p, lane_cap, laneR);
+  if (bpe && lg.version == 2) encode_bpe_lane2_kernel<<<grid, lane_threads, smem, st>>>(M, B, d_lane_slabs.p, lane_cap);
+  else if (bpe) encode_bpe_lane_kernel<<<grid, lane_threads, smem, st>>>(M, B, d_lane_slabs.p, lane_cap);
+  else encode_unigram_lane_kernel<<<grid, lane_threads, smem, st>>>(M, B, d_lane_slabs.p, lane_cap, lg.R);
   CUDA_TRY(cudaGetLastError());
   ++last_launches;
   CUDA_TRY(cudaEventRecord(ev[1], st));
@@ -1369,6 +1537,8 @@ int spm_engine::run_nbest(const char *bytes, const uint64_t *offsets, size_t n, 
     B.bytes = d_bytes.p - base;
     B.offsets = d_offsets.p;
     B.n = static_cast<uint32_t>(n);
+    B.off_lo = 0;
+    B.off_hi = ~0ull;
     B.work_counter = d_ctrl32.p + 4;
     B.status = d_ctrl32.p;
     NbestOut O{};
@@ -1443,6 +1613,8 @@ static int create_common(spm_engine *e, int device, spm_engine **out) {
   e->sm_count = prop.multiProcessorCount;
   if (const char *v = getenv("SPM_B200_SORT")) e->sort_by_length = atoi(v) != 0;  // A/B knob for profiles/
   if (const char *v = getenv("SPM_B200_FUSED")) e->fused_host_path = atoi(v) != 0;
+  if (const char *v = getenv("SPM_B200_FASTWORDS")) e->fast_words = atoi(v) != 0;
+  if (const char *v = getenv("SPM_B200_BPE_LANE_V")) e->bpe_lane_version = atoi(v);
   e->smem_optin = prop.sharedMemPerBlockOptin;
   if (cudaSetDevice(device) != cudaSuccess) return fail(SPM_ERR_CUDA, "cudaSetDevice failed");
   int rc = e->build_tables();
@@ -1501,7 +1673,7 @@ void spm_engine_destroy(spm_engine *e) {
   if (e->stream) cudaStreamSynchronize(e->stream);
   e->d_link.release(); e->d_val.release(); e->d_user_link.release(); e->d_cm_units.release(); e->d_cm_lead.release();
   e->d_cm_pair.release(); e->d_id.release(); e->d_cm_solo.release(); e->d_byte_to_id.release(); e->d_cm_targets.release();
-  e->d_types.release(); e->d_scores.release(); e->d_bytes.release(); e->d_tmp_norm.release(); e->d_norm.release();
+  e->d_types.release(); e->d_scores.release(); e->d_word_safe.release(); e->d_word_fast.release(); e->d_bytes.release(); e->d_tmp_norm.release(); e->d_norm.release();
   e->d_long_scratch.release(); e->d_offsets.release(); e->d_tmp_ids.release(); e->d_ids.release();
   e->d_tmp_tok_end.release(); e->d_tok_end.release(); e->d_tmp_n2o.release(); e->d_n2o.release();
   e->d_sent_count.release(); e->d_norm_len.release(); e->d_deferred.release(); e->d_deferred2.release(); e->d_long_list.release();

@@ -2,8 +2,10 @@
 #include "host/sentencepiece_processor.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cstring>
 #include <fstream>
+#include <functional>
 #include <set>
 #include <sstream>
 #include <unordered_map>
@@ -21,12 +23,19 @@ struct SentencePieceProcessor::Impl {
 };
 
 namespace {
+std::atomic<unsigned int> g_seed{0};
+std::atomic<bool> g_seed_set{false};
 util::Status Internal(const std::string &m) { return util::Status(util::StatusCode::kInternal, m); }
 util::Status FromEngine(const spm_engine *e, int rc) {
   if (rc == 0) return util::OkStatus();
   return Internal(std::string("spm_b200(") + std::to_string(rc) + "): " + spm_last_error(e));
 }
 }  // namespace
+
+void SetRandomGeneratorSeed(unsigned int seed) {
+  g_seed = seed;
+  g_seed_set = true;
+}
 
 SentencePieceProcessor::SentencePieceProcessor() : impl_(new Impl) {}
 SentencePieceProcessor::~SentencePieceProcessor() {
@@ -63,7 +72,42 @@ util::Status SentencePieceProcessor::LoadFromSerializedProto(std::string_view se
   }
   impl_->loaded_types = m.types;
   extra_.clear();
+  seeded_ = false;
   return util::OkStatus();
+}
+
+bool SentencePieceProcessor::IsControl(int id) const {
+  return id >= 0 && id < GetPieceSize() && impl_->model.types[id] == SPM_CONTROL;
+}
+
+// the reference's generator is thread_local and takes the global seed when it is first used (util.cc:202-204)
+void SentencePieceProcessor::SeedOnce() const {
+  if (seeded_) return;
+  seeded_ = true;
+  if (g_seed_set) spm_set_random_seed(engine_, g_seed);
+}
+
+util::Status SentencePieceProcessor::LoadVocabulary(std::string_view filename, int threshold) {
+  if (!engine_) return status();
+  std::ifstream f(std::string(filename), std::ios::binary);
+  if (!f) return util::Status(util::StatusCode::kNotFound, "\"" + std::string(filename) + "\": No such file or directory");
+  std::vector<std::string> vocab;
+  std::string line;
+  while (std::getline(f, line)) {
+    const size_t tab = line.find('\t');
+    const std::string piece = line.substr(0, tab);
+    if (piece.empty()) return Internal("empty piece in the vocabulary file");
+    long freq = 1;
+    if (tab != std::string::npos) {
+      const std::string fs = line.substr(tab + 1, line.find('\t', tab + 1) - tab - 1);
+      char *end = nullptr;
+      freq = strtol(fs.c_str(), &end, 10);
+      if (fs.empty() || *end) return Internal("Could not parse the frequency");
+    }
+    if (freq >= threshold) vocab.push_back(piece);
+  }
+  std::vector<std::string_view> views(vocab.begin(), vocab.end());
+  return SetVocabulary(views);
 }
 
 int SentencePieceProcessor::GetPieceSize() const { return static_cast<int>(impl_->pieces.size()); }
@@ -207,17 +251,35 @@ util::Status SentencePieceProcessor::Encode(const std::vector<std::string_view> 
   const auto st = EncodePacked(bytes.data(), offs.data(), inputs.size(), &out, &oo);
   if (!st.ok()) return st;
   ids->resize(inputs.size());
-  const int bos = PieceToId(impl_->model.bos_piece), eos = PieceToId(impl_->model.eos_piece);
   for (size_t i = 0; i < inputs.size(); ++i) {
     auto &v = (*ids)[i];
     v.assign(out + oo[i], out + oo[i + 1]);
-    for (const auto o : extra_) {  // ApplyExtraOptions, sentencepiece_processor.cc:1019-1064
-      if (o == REVERSE) std::reverse(v.begin(), v.end());
-      else if (o == EOS) v.push_back(eos);
-      else if (o == BOS) v.insert(v.begin(), bos);
-    }
+    ApplyExtraIds(&v);
   }
   return util::OkStatus();
+}
+
+// ApplyExtraOptions, sentencepiece_processor.cc:1019-1064
+void SentencePieceProcessor::ApplyExtraIds(std::vector<int> *v) const {
+  if (extra_.empty()) return;
+  const int bos = PieceToId(impl_->model.bos_piece), eos = PieceToId(impl_->model.eos_piece);
+  for (const auto o : extra_) {
+    if (o == REVERSE) std::reverse(v->begin(), v->end());
+    else if (o == EOS) v->push_back(eos);
+    else if (o == BOS) v->insert(v->begin(), bos);
+  }
+}
+void SentencePieceProcessor::ApplyExtraPieces(std::vector<std::string> *v, std::vector<int> *pid) const {
+  if (extra_.empty()) return;
+  const int bos = PieceToId(impl_->model.bos_piece), eos = PieceToId(impl_->model.eos_piece);
+  for (const auto o : extra_) {
+    if (o == REVERSE) { std::reverse(v->begin(), v->end()); std::reverse(pid->begin(), pid->end()); }
+    else if (o == EOS) { v->push_back(impl_->model.eos_piece); pid->push_back(eos); }
+    else if (o == BOS) { v->insert(v->begin(), impl_->model.bos_piece); pid->insert(pid->begin(), bos); }
+    else if (o == UNK_PIECE)
+      for (size_t k = 0; k < v->size(); ++k)
+        if ((*pid)[k] == unk_id_) (*v)[k] = impl_->model.unk_piece;
+  }
 }
 
 util::Status SentencePieceProcessor::Encode(const std::vector<std::string_view> &inputs,
@@ -235,7 +297,6 @@ util::Status SentencePieceProcessor::Encode(const std::vector<std::string_view> 
   const int rc = spm_encode_spans(engine_, bytes.data(), offs.data(), inputs.size(), &ids, &tok_end, &ido, &norm, &no, &n2o);
   if (rc) return FromEngine(engine_, rc);
   pieces->resize(inputs.size());
-  const int bos = PieceToId(impl_->model.bos_piece), eos = PieceToId(impl_->model.eos_piece);
   std::vector<int> pid;
   for (size_t i = 0; i < inputs.size(); ++i) {
     auto &v = (*pieces)[i];
@@ -248,16 +309,238 @@ util::Status SentencePieceProcessor::Encode(const std::vector<std::string_view> 
       pid.push_back(ids[k]);
       begin = tok_end[k];
     }
-    for (const auto o : extra_) {  // ApplyExtraOptions, sentencepiece_processor.cc:1019-1064
-      if (o == REVERSE) { std::reverse(v.begin(), v.end()); std::reverse(pid.begin(), pid.end()); }
-      else if (o == EOS) { v.push_back(impl_->model.eos_piece); pid.push_back(eos); }
-      else if (o == BOS) { v.insert(v.begin(), impl_->model.bos_piece); pid.insert(pid.begin(), bos); }
-      else if (o == UNK_PIECE)
-        for (size_t k = 0; k < v.size(); ++k)
-          if (pid[k] == unk_id_) v[k] = impl_->model.unk_piece;
+    ApplyExtraPieces(&v, &pid);
+  }
+  return util::OkStatus();
+}
+
+// ---- n-best and sampling ----
+//
+// The engine returns id sequences.  The piece forms need, for every UNKNOWN token, its surface in the normalized
+// text (sentencepiece_processor.cc:609-621); it is recovered by laying the id sequence over the normalized text: a
+// known id must spell its piece (byte pieces their byte) at the current position, an unknown id covers one or more
+// whole characters none of which has a one-character piece of its own (only such characters get an UNK node,
+// unigram_model.cc:590-594), up to wherever the rest of the sequence fits.
+bool SentencePieceProcessor::PiecesFromIds(std::string_view norm, const int32_t *ids, size_t n,
+                                           std::vector<std::string> *pieces) const {
+  pieces->assign(n, std::string());
+  static const unsigned char kLen[16] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 2, 2, 3, 4};
+  const auto &m = impl_->model;
+  std::function<bool(size_t, size_t)> rec = [&](size_t k, size_t pos) -> bool {
+    if (k == n) return pos == norm.size();
+    const int id = ids[k];
+    if (id < 0 || id >= GetPieceSize()) return false;
+    const uint8_t t = m.types[id];
+    if (t == SPM_BYTE) {  // <0xXX>: one byte of the text
+      const std::string &p = impl_->pieces[id];
+      if (pos >= norm.size() || p.size() != 6) return false;
+      const int v = static_cast<int>(strtol(p.substr(3, 2).c_str(), nullptr, 16));
+      if (static_cast<unsigned char>(norm[pos]) != v) return false;
+      (*pieces)[k] = p;
+      return rec(k + 1, pos + 1);
+    }
+    if (id != unk_id_) {
+      const std::string &p = impl_->pieces[id];
+      if (norm.compare(pos, p.size(), p) != 0) return false;
+      (*pieces)[k] = p;
+      return rec(k + 1, pos + p.size());
+    }
+    size_t end = pos;
+    while (end < norm.size()) {
+      const size_t cl = std::min<size_t>(kLen[static_cast<unsigned char>(norm[end]) >> 4], norm.size() - end);
+      const auto it = impl_->piece_to_id.find(std::string(norm.substr(end, cl)));
+      if (it != impl_->piece_to_id.end()) {
+        const uint8_t ct = m.types[it->second];
+        if (ct == SPM_NORMAL || ct == SPM_USER_DEFINED) break;  // this character has its own piece: no UNK node
+      }
+      end += cl;
+      (*pieces)[k].assign(norm.substr(pos, end - pos));
+      if (rec(k + 1, end)) return true;
+    }
+    return false;
+  };
+  return rec(0, 0);
+}
+
+util::Status SentencePieceProcessor::NBestEncode(const std::vector<std::string_view> &inputs, int nbest_size,
+                                                 std::vector<std::vector<std::vector<int>>> *ids) const {
+  if (!engine_) return status();
+  if (!ids) return Internal("output container is null");
+  ids->clear();
+  std::string bytes;
+  std::vector<uint64_t> offs;
+  Pack(inputs, &bytes, &offs);
+  const int32_t *out;
+  const uint64_t *co;
+  const float *sc;
+  const uint32_t *nc;
+  const int rc = spm_nbest_encode(engine_, bytes.data(), offs.data(), inputs.size(), nbest_size, &out, &co, &sc, &nc);
+  if (rc) return FromEngine(engine_, rc);
+  const size_t K = static_cast<size_t>(std::max(1, std::min(nbest_size, 1024)));
+  ids->resize(inputs.size());
+  for (size_t i = 0; i < inputs.size(); ++i) {
+    auto &cands = (*ids)[i];
+    cands.resize(nc[i]);
+    for (uint32_t c = 0; c < nc[i]; ++c) {
+      cands[c].assign(out + co[i * K + c], out + co[i * K + c + 1]);
+      ApplyExtraIds(&cands[c]);
     }
   }
   return util::OkStatus();
+}
+
+util::Status SentencePieceProcessor::NBestEncode(const std::vector<std::string_view> &inputs, int nbest_size,
+                                                 std::vector<std::vector<std::vector<std::string>>> *pieces) const {
+  if (!engine_) return status();
+  if (!pieces) return Internal("output container is null");
+  pieces->clear();
+  std::string bytes;
+  std::vector<uint64_t> offs;
+  Pack(inputs, &bytes, &offs);
+  // normalized text first (the spans call), then the candidates: both results live in engine buffers of their own
+  const int32_t *sids;
+  const uint32_t *tok_end, *n2o;
+  const uint64_t *ido, *no;
+  const char *norm;
+  int rc = spm_encode_spans(engine_, bytes.data(), offs.data(), inputs.size(), &sids, &tok_end, &ido, &norm, &no, &n2o);
+  if (rc) return FromEngine(engine_, rc);
+  std::vector<std::string> norms(inputs.size());
+  for (size_t i = 0; i < inputs.size(); ++i) norms[i].assign(norm + no[i], norm + no[i + 1]);
+  const int32_t *out;
+  const uint64_t *co;
+  const float *sc;
+  const uint32_t *nc;
+  rc = spm_nbest_encode(engine_, bytes.data(), offs.data(), inputs.size(), nbest_size, &out, &co, &sc, &nc);
+  if (rc) return FromEngine(engine_, rc);
+  const size_t K = static_cast<size_t>(std::max(1, std::min(nbest_size, 1024)));
+  pieces->resize(inputs.size());
+  std::vector<int> pid;
+  for (size_t i = 0; i < inputs.size(); ++i) {
+    auto &cands = (*pieces)[i];
+    cands.resize(nc[i]);
+    for (uint32_t c = 0; c < nc[i]; ++c) {
+      const uint64_t lo = co[i * K + c], hi = co[i * K + c + 1];
+      if (!PiecesFromIds(norms[i], out + lo, hi - lo, &cands[c]))
+        return Internal("all normalized characters are not consumed.");  // sentencepiece_processor.cc:628-629
+      pid.assign(out + lo, out + hi);
+      ApplyExtraPieces(&cands[c], &pid);
+    }
+  }
+  return util::OkStatus();
+}
+
+util::Status SentencePieceProcessor::SampleEncode(const std::vector<std::string_view> &inputs, int nbest_size, float alpha,
+                                                  std::vector<std::vector<int>> *ids) const {
+  if (!engine_) return status();
+  if (!ids) return Internal("output container is null");
+  ids->clear();
+  SeedOnce();
+  std::string bytes;
+  std::vector<uint64_t> offs;
+  Pack(inputs, &bytes, &offs);
+  const int32_t *out;
+  const uint64_t *oo;
+  const int rc = spm_sample_encode_ids(engine_, bytes.data(), offs.data(), inputs.size(), nbest_size, alpha, &out, &oo);
+  if (rc) return FromEngine(engine_, rc);
+  ids->resize(inputs.size());
+  for (size_t i = 0; i < inputs.size(); ++i) {
+    (*ids)[i].assign(out + oo[i], out + oo[i + 1]);
+    ApplyExtraIds(&(*ids)[i]);
+  }
+  return util::OkStatus();
+}
+
+util::Status SentencePieceProcessor::SampleEncode(const std::vector<std::string_view> &inputs, int nbest_size, float alpha,
+                                                  std::vector<std::vector<std::string>> *pieces) const {
+  if (!engine_) return status();
+  if (!pieces) return Internal("output container is null");
+  pieces->clear();
+  SeedOnce();
+  std::string bytes;
+  std::vector<uint64_t> offs;
+  Pack(inputs, &bytes, &offs);
+  const int32_t *sids;
+  const uint32_t *tok_end, *n2o;
+  const uint64_t *ido, *no;
+  const char *norm;
+  int rc = spm_encode_spans(engine_, bytes.data(), offs.data(), inputs.size(), &sids, &tok_end, &ido, &norm, &no, &n2o);
+  if (rc) return FromEngine(engine_, rc);
+  std::vector<std::string> norms(inputs.size());
+  for (size_t i = 0; i < inputs.size(); ++i) norms[i].assign(norm + no[i], norm + no[i + 1]);
+  const int32_t *out;
+  const uint64_t *oo;
+  rc = spm_sample_encode_ids(engine_, bytes.data(), offs.data(), inputs.size(), nbest_size, alpha, &out, &oo);
+  if (rc) return FromEngine(engine_, rc);
+  pieces->resize(inputs.size());
+  std::vector<int> pid;
+  for (size_t i = 0; i < inputs.size(); ++i) {
+    if (!PiecesFromIds(norms[i], out + oo[i], oo[i + 1] - oo[i], &(*pieces)[i]))
+      return Internal("all normalized characters are not consumed.");
+    pid.assign(out + oo[i], out + oo[i + 1]);
+    ApplyExtraPieces(&(*pieces)[i], &pid);
+  }
+  return util::OkStatus();
+}
+
+util::Status SentencePieceProcessor::NBestEncode(std::string_view input, int nbest_size,
+                                                 std::vector<std::vector<int>> *ids) const {
+  if (!engine_) return status();
+  if (!ids) return Internal("output container is null");
+  std::vector<std::vector<std::vector<int>>> out;
+  const auto st = NBestEncode(std::vector<std::string_view>{input}, nbest_size, &out);
+  if (!st.ok()) return st;
+  *ids = std::move(out[0]);
+  return util::OkStatus();
+}
+util::Status SentencePieceProcessor::NBestEncode(std::string_view input, int nbest_size,
+                                                 std::vector<std::vector<std::string>> *pieces) const {
+  if (!engine_) return status();
+  if (!pieces) return Internal("output container is null");
+  std::vector<std::vector<std::vector<std::string>>> out;
+  const auto st = NBestEncode(std::vector<std::string_view>{input}, nbest_size, &out);
+  if (!st.ok()) return st;
+  *pieces = std::move(out[0]);
+  return util::OkStatus();
+}
+util::Status SentencePieceProcessor::SampleEncode(std::string_view input, int nbest_size, float alpha,
+                                                  std::vector<int> *ids) const {
+  if (!engine_) return status();
+  if (!ids) return Internal("output container is null");
+  std::vector<std::vector<int>> out;
+  const auto st = SampleEncode(std::vector<std::string_view>{input}, nbest_size, alpha, &out);
+  if (!st.ok()) return st;
+  *ids = std::move(out[0]);
+  return util::OkStatus();
+}
+util::Status SentencePieceProcessor::SampleEncode(std::string_view input, int nbest_size, float alpha,
+                                                  std::vector<std::string> *pieces) const {
+  if (!engine_) return status();
+  if (!pieces) return Internal("output container is null");
+  std::vector<std::vector<std::string>> out;
+  const auto st = SampleEncode(std::vector<std::string_view>{input}, nbest_size, alpha, &out);
+  if (!st.ok()) return st;
+  *pieces = std::move(out[0]);
+  return util::OkStatus();
+}
+std::vector<std::vector<std::string>> SentencePieceProcessor::NBestEncodeAsPieces(std::string_view input, int nbest_size) const {
+  std::vector<std::vector<std::string>> out;
+  NBestEncode(input, nbest_size, &out).IgnoreError();
+  return out;
+}
+std::vector<std::vector<int>> SentencePieceProcessor::NBestEncodeAsIds(std::string_view input, int nbest_size) const {
+  std::vector<std::vector<int>> out;
+  NBestEncode(input, nbest_size, &out).IgnoreError();
+  return out;
+}
+std::vector<std::string> SentencePieceProcessor::SampleEncodeAsPieces(std::string_view input, int nbest_size, float alpha) const {
+  std::vector<std::string> out;
+  SampleEncode(input, nbest_size, alpha, &out).IgnoreError();
+  return out;
+}
+std::vector<int> SentencePieceProcessor::SampleEncodeAsIds(std::string_view input, int nbest_size, float alpha) const {
+  std::vector<int> out;
+  SampleEncode(input, nbest_size, alpha, &out).IgnoreError();
+  return out;
 }
 
 util::Status SentencePieceProcessor::Encode(std::string_view input, std::vector<int> *ids) const {

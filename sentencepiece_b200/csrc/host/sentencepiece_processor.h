@@ -7,7 +7,8 @@
 // Encode(pieces) :295, Encode(ids) :299, EncodeAsPieces :453, EncodeAsIds :458) --
 // so a caller such as spm_encode compiles against it unchanged, and adds the batch
 // overloads that a GPU needs.  Single-sentence calls are batches of one.
-// Only the encode path is here: training, decoding, n-best/sampling stay the reference's.
+// N-best and sampling (NBestEncode :318-324, SampleEncode :345-351, the value-returning forms :465-481,
+// SetRandomGeneratorSeed :731) ride on the engine's n-best / sampling kernels; training stays the reference's.
 #ifndef SPM_B200_HOST_SENTENCEPIECE_PROCESSOR_H_
 #define SPM_B200_HOST_SENTENCEPIECE_PROCESSOR_H_
 
@@ -61,6 +62,8 @@ class SentencePieceProcessor {
   util::Status SetEncodeExtraOptions(std::string_view extra_option);
   util::Status SetVocabulary(const std::vector<std::string_view> &valid_vocab);
   util::Status ResetVocabulary();
+  // "<piece>\t<freq>" lines; pieces with freq < threshold become UNUSED (sentencepiece_processor.cc:342-365)
+  util::Status LoadVocabulary(std::string_view filename, int threshold);
 
   // ---- single sentence (reference signatures) ----
   util::Status Encode(std::string_view input, std::vector<std::string> *pieces) const;
@@ -68,10 +71,32 @@ class SentencePieceProcessor {
   std::vector<std::string> EncodeAsPieces(std::string_view input) const;
   std::vector<int> EncodeAsIds(std::string_view input) const;
 
+  // ---- n-best and sampling, single sentence (reference signatures, sentencepiece_processor.h:318-351,465-481).
+  //      Errors like the reference: n-best is not available for BPE models (sentencepiece_processor.cc:662-663),
+  //      nbest_size > 512 fails SampleEncode (:683). ----
+  util::Status NBestEncode(std::string_view input, int nbest_size, std::vector<std::vector<std::string>> *pieces) const;
+  util::Status NBestEncode(std::string_view input, int nbest_size, std::vector<std::vector<int>> *ids) const;
+  util::Status SampleEncode(std::string_view input, int nbest_size, float alpha, std::vector<std::string> *pieces) const;
+  util::Status SampleEncode(std::string_view input, int nbest_size, float alpha, std::vector<int> *ids) const;
+  std::vector<std::vector<std::string>> NBestEncodeAsPieces(std::string_view input, int nbest_size) const;
+  std::vector<std::vector<int>> NBestEncodeAsIds(std::string_view input, int nbest_size) const;
+  std::vector<std::string> SampleEncodeAsPieces(std::string_view input, int nbest_size, float alpha) const;
+  std::vector<int> SampleEncodeAsIds(std::string_view input, int nbest_size, float alpha) const;
+
   // ---- batch (what the reference's Python layer does with a thread pool,
   //      python/src/sentencepiece/sentencepiece.i:245-267) ----
   util::Status Encode(const std::vector<std::string_view> &inputs, std::vector<std::vector<int>> *ids) const;
   util::Status Encode(const std::vector<std::string_view> &inputs, std::vector<std::vector<std::string>> *pieces) const;
+  // one device call for all sentences; the draws of SampleEncode are taken in input order on one generator, which is
+  // what a single-threaded loop over the reference's SampleEncode does
+  util::Status NBestEncode(const std::vector<std::string_view> &inputs, int nbest_size,
+                           std::vector<std::vector<std::vector<int>>> *ids) const;
+  util::Status NBestEncode(const std::vector<std::string_view> &inputs, int nbest_size,
+                           std::vector<std::vector<std::vector<std::string>>> *pieces) const;
+  util::Status SampleEncode(const std::vector<std::string_view> &inputs, int nbest_size, float alpha,
+                            std::vector<std::vector<int>> *ids) const;
+  util::Status SampleEncode(const std::vector<std::string_view> &inputs, int nbest_size, float alpha,
+                            std::vector<std::vector<std::string>> *pieces) const;
   // zero-copy form: packed input, packed output owned by the engine until the next call
   util::Status EncodePacked(const char *bytes, const uint64_t *offsets, size_t n, const int32_t **ids,
                             const uint64_t **id_offsets) const;
@@ -88,6 +113,7 @@ class SentencePieceProcessor {
   int PieceToId(std::string_view piece) const;
   const std::string &IdToPiece(int id) const;
   bool IsUnknown(int id) const { return id == unk_id_; }
+  bool IsControl(int id) const;
   int unk_id() const { return unk_id_; }
   int bos_id() const;
   int eos_id() const;
@@ -100,7 +126,17 @@ class SentencePieceProcessor {
   int device_ = 0;
   int unk_id_ = -1;
   std::vector<ExtraOption> extra_;
+  mutable bool seeded_ = false;  // the engine's generator took the global seed (first sampling call)
+  void SeedOnce() const;
+  void ApplyExtraIds(std::vector<int> *v) const;
+  void ApplyExtraPieces(std::vector<std::string> *v, std::vector<int> *pid) const;
+  // pieces of an id sequence over the sentence's normalized text (unknown tokens keep their surface)
+  bool PiecesFromIds(std::string_view normalized, const int32_t *ids, size_t n, std::vector<std::string> *pieces) const;
 };
+
+// sentencepiece_processor.h:731 / util.cc:23-31: the seed every generator created afterwards starts from; this
+// layer's generators live in the engines and take it at their first sampling call
+void SetRandomGeneratorSeed(unsigned int seed);
 
 }  // namespace sentencepiece
 #endif

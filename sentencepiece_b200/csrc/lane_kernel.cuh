@@ -361,6 +361,123 @@ __device__ __forceinline__ uint32_t lane_normalize(const KModel &M, const uint8_
   return out;
 }
 
+// K4: back-trace + id path of PopulateSentencePieceText (sentencepiece_processor.cc:547-636) over a lane's
+// back-pointer log: two coalesced backward scans (count, then write) around one warp-aggregated claim of output space.
+// entry t (t = 0..nlog-1) = plen (6 bits) << 24 | (previous char length - 1) << 22 | trie unit (kLaneUnk: UNK piece);
+// bit 31 (lane2 whole-word entries): the previous logged position is plen bytes back.
+__device__ __forceinline__ void lane_finish(const KModel &M, const KBatch &B, const LaneCtx &c, uint32_t n, uint32_t nlog,
+                                            uint32_t lane, bool have, bool defer, uint32_t sent, bool bf) {
+  // ---------------- K4: coalesced backward scans of the log ----------------
+  // entry t (t = 0..nlog-1) belongs to the (t+1)-th character boundary p_t; the character
+  // before p_t has (entry>>22 & 3) + 1 bytes, so positions are recovered going backwards.
+  const uint32_t max_log = __reduce_max_sync(0xFFFFFFFFu, nlog);
+  uint32_t count = 0;
+  {
+    uint32_t pos_b = n, want = n;
+    bool prev_unk = false;
+    for (uint32_t tb = (max_log + 3u) & ~3u; tb > 0; tb -= 4) {
+      uint32_t ev[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {  // four independent, coalesced loads per trip
+        const uint32_t t = tb - 1 - j;
+        ev[j] = t < nlog ? c.log[static_cast<size_t>(t) * 32] : 0u;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t t = tb - 1 - j;
+        if (t < nlog) {
+          const uint32_t e = ev[j];
+          if (pos_b == want) {
+            const uint32_t plen = (e >> 24) & 63u;
+            const bool isunk = (e & 0x3FFFFFu) == kLaneUnk;
+            if (bf) count += isunk ? plen : 1u;
+            else count += !(isunk && prev_unk);
+            prev_unk = isunk;
+            want -= plen;
+          }
+          pos_b -= (e >> 31) ? ((e >> 24) & 63u) : ((e >> 22) & 3u) + 1u;  // whole-word entries (lane2) step back plen bytes
+        }
+      }
+    }
+    if (n && want != 0) { atomicOr(B.status + 1, 1u); count = 0; }
+  }
+  // one claim of output space per warp
+  uint32_t incl = count;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+    if (lane >= static_cast<uint32_t>(d)) incl += t;
+  }
+  const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+  unsigned long long pos = 0;
+  if (lane == 0 && total) {
+    pos = atomicAdd(B.cursor, static_cast<unsigned long long>(total));
+    if (pos + total > B.tmp_cap) atomicOr(B.status + 2, 1u);
+  }
+  pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
+  const bool room = pos + total <= B.tmp_cap;
+  pos += incl - count;
+  if (have && !defer) {
+    B.sent_start[sent] = pos;
+    B.sent_count[sent] = room ? count : 0u;
+  }
+  // second backward scan: write ids from the end
+  if (room) {
+    uint32_t pos_b = n, want = n, w = count;
+    bool prev_unk = false;
+    for (uint32_t tb = (max_log + 3u) & ~3u; tb > 0; tb -= 4) {
+      uint32_t ev[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t t = tb - 1 - j;
+        ev[j] = t < nlog ? c.log[static_cast<size_t>(t) * 32] : 0u;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+      const uint32_t t = tb - 1 - j;
+      if (t < nlog && w > 0) {
+        const uint32_t e = ev[j];
+        if (pos_b == want) {
+          const uint32_t plen = (e >> 24) & 63u;
+          const uint32_t idx = e & 0x3FFFFFu;
+          const bool isunk = idx == kLaneUnk;
+          if (isunk) {
+            if (bf) {
+              for (uint32_t i = 0; i < plen; ++i) {
+                const uint32_t kk = want - 1 - i;
+                const uint32_t ch = (c.text_w[static_cast<size_t>(kk >> 2) * 32] >> ((kk & 3u) * 8u)) & 0xFFu;
+                B.tmp_ids[pos + (--w)] = __ldg(M.byte_to_id + ch);
+              }
+            } else if (!prev_unk) {
+              B.tmp_ids[pos + (--w)] = M.unk_id;
+            }
+          } else {
+            B.tmp_ids[pos + (--w)] = __ldg(M.trie_id + idx);
+          }
+          prev_unk = isunk;
+          want -= plen;
+        }
+        pos_b -= (e >> 31) ? ((e >> 24) & 63u) : ((e >> 22) & 3u) + 1u;  // whole-word entries (lane2) step back plen bytes
+      }
+      }
+    }
+  }
+}
+
+// shared memory per warp: ring of R slots, each {score f32, back-pointer u32, position tag u16} x 32 lanes
+__host__ __device__ inline uint32_t lane_ring_bytes(uint32_t R) { return R * 32u * (4u + 4u + 2u); }
+
+constexpr uint32_t kLogWordStep = 1u << 31;  // log entry: the previous logged position is plen bytes back (whole word)
+constexpr uint32_t kWsWord = 0x8196E2u;      // U+2581 as the low three bytes of a little-endian word
+
+// Whole-word shortcut (kFlagFastWords; engine.cu upload_word_safe has the proof): when no piece contains U+2581
+// past its first byte, every segmentation has a token boundary in front of every U+2581, so the Viterbi problem of
+// a word [b, e) (U+2581 + the characters up to the next U+2581) only sees the rest of the sentence through the
+// float best_path_score at b.  If the word IS a piece P whose score beats the best split of the word by more than
+// the rounding noise the float recurrence can accumulate up to position e (M.word_safe[unit] = the largest such e),
+// the reference necessarily ends the word with P alone.  The walk from b reaches e on P's node, P has just been
+// relaxed into e exactly as the reference relaxes it (first candidate of e), and the starts inside the word are
+// skipped: 73 % of the words of the English corpus, half of all character starts.
 __global__ void __launch_bounds__(1024, 1) encode_unigram_lane_kernel(const KModel M, const KBatch B, uint8_t *slabs,
                                                                        uint32_t cap, uint32_t R) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -372,10 +489,13 @@ __global__ void __launch_bounds__(1024, 1) encode_unigram_lane_kernel(const KMod
   const uint32_t warp_in_cta = threadIdx.x >> 5;
   const uint32_t warp_global = blockIdx.x * (blockDim.x >> 5) + warp_in_cta;
   LaneCtx c;
+  uint16_t *rp;  // ring position tags: a slot belongs to position p iff rp == p (no clearing, skipped positions
+                 // of whole words leave stale slots behind that simply fail the test)
   {
-    uint8_t *ring = rings + static_cast<size_t>(warp_in_cta) * (R * 32 * 8);
+    uint8_t *ring = rings + static_cast<size_t>(warp_in_cta) * lane_ring_bytes(R);
     c.rs = reinterpret_cast<float *>(ring) + lane;
     c.rb = reinterpret_cast<uint32_t *>(ring + R * 32 * 4) + lane;
+    rp = reinterpret_cast<uint16_t *>(ring + R * 32 * 8) + lane;
     uint8_t *slab = slabs + static_cast<size_t>(warp_global) * lane_slab_bytes(cap);
     c.text_w = reinterpret_cast<uint32_t *>(slab) + lane;
     c.log = reinterpret_cast<uint32_t *>(slab) + static_cast<size_t>(cap / 4 + kLaneTextSlack) * 32 + lane;
@@ -389,6 +509,8 @@ __global__ void __launch_bounds__(1024, 1) encode_unigram_lane_kernel(const KMod
   const uint32_t root = __ldg(&node2[0]).x;
   const bool bf = M.flags & kFlagByteFallback;
   const bool regular = M.flags & kFlagRegularScores;
+  const bool fastwords = M.flags & kFlagFastWords;
+  const uint32_t r_wrap = R * 32;
 
   for (;;) {
     uint32_t first = 0;
@@ -404,10 +526,10 @@ __global__ void __launch_bounds__(1024, 1) encode_unigram_lane_kernel(const KMod
     if (have) {
       const unsigned long long off = B.offsets[sent];
       const unsigned long long len64 = B.offsets[sent + 1] - off;
-      if (len64 > 4ull * cap) defer = true;
+      if (len64 > 4ull * cap || len64 > 0xFFF0ull || off < B.off_lo || off + len64 > B.off_hi) defer = true;
       else {
         n = lane_normalize(M, B.bytes + off, static_cast<uint32_t>(len64), c, cap);
-        if (n == 0xFFFFFFFFu) { defer = true; n = 0; }
+        if (n == 0xFFFFFFFFu || n >= 0xFFF0u) { defer = true; n = 0; }  // (positions are 16-bit ring tags)
       }
       if (defer) {
         const uint32_t slot = atomicAdd(B.status, 1u);
@@ -419,9 +541,10 @@ __global__ void __launch_bounds__(1024, 1) encode_unigram_lane_kernel(const KMod
     __syncwarp();
     // ---------------- K2: flat state machine, one trie transition per trip ----------------
     // text window: words w0..w3 = bytes [4*aw, 4*aw+16), aw = s >> 2; `cur` streams the bytes
-    // from the walk position k (low byte first).
-    uint32_t s = 0, ss = 0 /* ring slot of s */, k = 0, l = root, mblen = 1, nlog = 0;
+    // from the walk position k (low byte first).  ss = ring slot of s, times 32.
+    uint32_t s = 0, ss = 0, k = 0, l = root, lv = 0, mblen = 1, nlog = 0;
     bool has_single = false, done = n == 0;
+    bool wstart = true;  // s is the first character of a word (text start or U+2581)
     float base = 0.f;
     bool base_regular = regular;  // base == 0
     uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
@@ -437,7 +560,7 @@ __global__ void __launch_bounds__(1024, 1) encode_unigram_lane_kernel(const KMod
              (static_cast<unsigned long long>(w3 >> sh) << 32);
     };
     if (!done) {
-      for (uint32_t r = 0; r < R; ++r) c.rb[r * 32] = 0u;  // all positions unset
+      for (uint32_t r = 0; r < R; ++r) rp[r * 32] = 0xFFFFu;  // no slot belongs to a position of this sentence
       c.rs[0] = 0.f;
       w0 = c.text_w[0]; w1 = c.text_w[32]; w2 = c.text_w[64]; w3 = c.text_w[96];
       mblen = one_char_len(w0 & 0xFFu);
@@ -462,14 +585,14 @@ __global__ void __launch_bounds__(1024, 1) encode_unigram_lane_kernel(const KMod
           if ((nd.x & kLinkLabelMask) == ch) {
             ++k;
             l = nd.x;
+            lv = v;
             const uint32_t kind = (nd.x >> kLinkKindShift) & 3u;
             if (kind == kKindNormal || kind == kKindUserDefined) {
               const uint32_t plen = k - s;
-              uint32_t sl = ss + plen;
-              if (sl >= R) sl -= R;
-              sl *= 32;
+              uint32_t sl = ss + plen * 32u;
+              if (sl >= r_wrap) sl -= r_wrap;
               const float curs = c.rs[sl];
-              const bool unset = c.rb[sl] == 0u;
+              const bool unset = rp[sl] != k;
               float ns;
               bool better;
               if (kind == kKindNormal && base_regular) {
@@ -493,6 +616,7 @@ __global__ void __launch_bounds__(1024, 1) encode_unigram_lane_kernel(const KMod
               if (better) {
                 c.rs[sl] = ns;
                 c.rb[sl] = (plen << 24) | v;
+                rp[sl] = static_cast<uint16_t>(k);
               }
               has_single |= plen == mblen;
             }
@@ -509,34 +633,69 @@ __global__ void __launch_bounds__(1024, 1) encode_unigram_lane_kernel(const KMod
         }
         if (end_walk) {
           // the walk from s is over (traverse() == -2, or end of text)
-          uint32_t sl = ss + mblen;
-          if (sl >= R) sl -= R;
-          if (!has_single) {  // UNK edge, unigram_model.cc:995-1005
-            const float cand = __fadd_rn(M.unk_score, base);
-            if (c.rb[sl * 32] == 0u || cand > c.rs[sl * 32]) {
-              c.rs[sl * 32] = cand;
-              c.rb[sl * 32] = (mblen << 24) | kLaneUnk;
+          bool fast = false;
+          if (fastwords && wstart && k > s && ((l >> kLinkKindShift) & 3u) == kKindNormal) {
+            // the walk covered [s, k) and ended on a NORMAL piece: is k the end of the word, early enough to be safe?
+            bool wend = k >= n;
+            if (!wend && k + 3u <= n) {
+              const uint32_t o = k - ((s >> 2) << 2);
+              uint32_t b3;
+              if (o <= 13u) {
+                const uint32_t wi = o >> 2;
+                const uint32_t lo = wi == 0u ? w0 : (wi == 1u ? w1 : (wi == 2u ? w2 : w3));
+                const uint32_t hi = wi == 0u ? w1 : (wi == 1u ? w2 : (wi == 2u ? w3 : 0u));
+                b3 = __funnelshift_r(lo, hi, (o & 3u) * 8u) & 0xFFFFFFu;
+              } else {
+                b3 = 0;
+                for (uint32_t i = 0; i < 3u; ++i)
+                  b3 |= ((c.text_w[static_cast<size_t>((k + i) >> 2) * 32] >> (((k + i) & 3u) * 8u)) & 0xFFu) << (8u * i);
+              }
+              wend = b3 == kWsWord;
             }
+            fast = wend && k <= static_cast<uint32_t>(__ldg(M.word_safe + lv));
           }
-          // position s leaves the window; only character starts are ever targets, so its
-          // slot is the only one that has to be cleared for position s + R
-          c.rb[ss * 32] = 0u;
-          s += mblen;
-          ss = sl;
-          // position s is final: append (plen | previous char length | unit) to the log
-          c.log[static_cast<size_t>(nlog) * 32] = c.rb[ss * 32] | ((mblen - 1u) << 22);
+          const uint32_t s_old = s;
+          uint32_t steplog;
+          if (fast) {
+            // the piece was relaxed into k when the walk stepped onto its node; nothing else can win there
+            ss += (k - s) * 32u;
+            s = k;
+            steplog = kLogWordStep;
+          } else {
+            uint32_t sl = ss + mblen * 32u;
+            if (sl >= r_wrap) sl -= r_wrap;
+            if (!has_single) {  // UNK edge, unigram_model.cc:995-1005
+              const float cand = __fadd_rn(M.unk_score, base);
+              if (rp[sl] != s + mblen || cand > c.rs[sl]) {
+                c.rs[sl] = cand;
+                c.rb[sl] = (mblen << 24) | kLaneUnk;
+                rp[sl] = static_cast<uint16_t>(s + mblen);
+              }
+            }
+            ss = sl;
+            s += mblen;
+            steplog = (mblen - 1u) << 22;
+          }
+          if (ss >= r_wrap) ss -= r_wrap;
+          // position s is final: append (plen | previous char length or whole-word step | unit) to the log
+          c.log[static_cast<size_t>(nlog) * 32] = c.rb[ss] | steplog;
           ++nlog;
           if (s >= n) {
             done = true;
           } else {
-            base = c.rs[ss * 32];
+            base = c.rs[ss];
             base_regular = regular && (base == 0.f || (fabsf(base) >= 0.0009765625f && fabsf(base) < 262144.f));
             // slide the text window so that it is anchored at s; prefetch the new tail word
-            if ((s >> 2) != ((s - mblen) >> 2)) {
+            const uint32_t jw = (s >> 2) - (s_old >> 2);
+            if (jw == 1u) {
               w0 = w1; w1 = w2; w2 = w3;
               w3 = c.text_w[static_cast<size_t>((s >> 2) + 3) * 32];
+            } else if (jw != 0u) {
+              const uint32_t *tw = c.text_w + static_cast<size_t>(s >> 2) * 32;
+              w0 = tw[0]; w1 = tw[32]; w2 = tw[64]; w3 = tw[96];
             }
             cur = window_low();
+            wstart = (static_cast<uint32_t>(cur) & 0xFFFFFFu) == kWsWord;
             mblen = one_char_len(static_cast<uint32_t>(cur) & 0xFFu);
             if (mblen > n - s) mblen = n - s;
             k = s;
@@ -546,101 +705,7 @@ __global__ void __launch_bounds__(1024, 1) encode_unigram_lane_kernel(const KMod
         }
       }
     }
-    // ---------------- K4: coalesced backward scans of the log ----------------
-    // entry t (t = 0..nlog-1) belongs to the (t+1)-th character boundary p_t; the character
-    // before p_t has (entry>>22 & 3) + 1 bytes, so positions are recovered going backwards.
-    const uint32_t max_log = __reduce_max_sync(0xFFFFFFFFu, nlog);
-    uint32_t count = 0;
-    {
-      uint32_t pos_b = n, want = n;
-      bool prev_unk = false;
-      for (uint32_t tb = (max_log + 3u) & ~3u; tb > 0; tb -= 4) {
-        uint32_t ev[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {  // four independent, coalesced loads per trip
-          const uint32_t t = tb - 1 - j;
-          ev[j] = t < nlog ? c.log[static_cast<size_t>(t) * 32] : 0u;
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t t = tb - 1 - j;
-          if (t < nlog) {
-            const uint32_t e = ev[j];
-            if (pos_b == want) {
-              const uint32_t plen = e >> 24;
-              const bool isunk = (e & 0x3FFFFFu) == kLaneUnk;
-              if (bf) count += isunk ? plen : 1u;
-              else count += !(isunk && prev_unk);
-              prev_unk = isunk;
-              want -= plen;
-            }
-            pos_b -= ((e >> 22) & 3u) + 1u;
-          }
-        }
-      }
-      if (n && want != 0) { atomicOr(B.status + 1, 1u); count = 0; }
-    }
-    // one claim of output space per warp
-    uint32_t incl = count;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-      if (lane >= static_cast<uint32_t>(d)) incl += t;
-    }
-    const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-    unsigned long long pos = 0;
-    if (lane == 0 && total) {
-      pos = atomicAdd(B.cursor, static_cast<unsigned long long>(total));
-      if (pos + total > B.tmp_cap) atomicOr(B.status + 2, 1u);
-    }
-    pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
-    const bool room = pos + total <= B.tmp_cap;
-    pos += incl - count;
-    if (have && !defer) {
-      B.sent_start[sent] = pos;
-      B.sent_count[sent] = room ? count : 0u;
-    }
-    // second backward scan: write ids from the end
-    if (room) {
-      uint32_t pos_b = n, want = n, w = count;
-      bool prev_unk = false;
-      for (uint32_t tb = (max_log + 3u) & ~3u; tb > 0; tb -= 4) {
-        uint32_t ev[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t t = tb - 1 - j;
-          ev[j] = t < nlog ? c.log[static_cast<size_t>(t) * 32] : 0u;
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-        const uint32_t t = tb - 1 - j;
-        if (t < nlog && w > 0) {
-          const uint32_t e = ev[j];
-          if (pos_b == want) {
-            const uint32_t plen = e >> 24;
-            const uint32_t idx = e & 0x3FFFFFu;
-            const bool isunk = idx == kLaneUnk;
-            if (isunk) {
-              if (bf) {
-                for (uint32_t i = 0; i < plen; ++i) {
-                  const uint32_t kk = want - 1 - i;
-                  const uint32_t ch = (c.text_w[static_cast<size_t>(kk >> 2) * 32] >> ((kk & 3u) * 8u)) & 0xFFu;
-                  B.tmp_ids[pos + (--w)] = __ldg(M.byte_to_id + ch);
-                }
-              } else if (!prev_unk) {
-                B.tmp_ids[pos + (--w)] = M.unk_id;
-              }
-            } else {
-              B.tmp_ids[pos + (--w)] = __ldg(M.trie_id + idx);
-            }
-            prev_unk = isunk;
-            want -= plen;
-          }
-          pos_b -= ((e >> 22) & 3u) + 1u;
-        }
-        }
-      }
-    }
+    lane_finish(M, B, c, n, nlog, lane, have, defer, sent, bf);  // K4
     lane_drain(B, first, lane);  // K6 (fused host path only)
     __syncwarp();
   }
