@@ -145,13 +145,36 @@ int spm_nbest_encode(spm_engine *e, const char *bytes, const uint64_t *offsets, 
 int spm_set_random_seed(spm_engine *e, uint32_t seed);
 
 /* Replaces SentencePieceProcessor::SampleEncode(input, nbest_size, alpha, ids)
- * (src/sentencepiece_processor.cc:678-722) for nbest_size in [0, 512]: nbest_size of 0 or 1 is
- * the plain Encode; otherwise the n-best list is computed on the GPU and one candidate is drawn
- * with probability proportional to exp(alpha * score) exactly as the reference does
- * (log-sum-exp in double, std::discrete_distribution on std::mt19937).  nbest_size < 0
- * (forward-filtering/backward-sampling) and BPE-dropout are not on the accelerated path. */
+ * (src/sentencepiece_processor.cc:678-722), nbest_size <= 512 like the reference:
+ *   nbest_size of 0 or 1: the plain Encode (:695-698);
+ *   nbest_size > 1: the n-best list is computed on the GPU and one candidate is drawn with probability
+ *     proportional to exp(alpha * score) exactly as the reference does (log-sum-exp in double,
+ *     std::discrete_distribution on std::mt19937);
+ *   nbest_size < 0: forward-filtering / backward-sampling over the whole lattice (:689-693 ->
+ *     unigram::Model::SampleEncode, src/unigram_model.cc:511-542,722-739): the lattice and the forward
+ *     scores come from the GPU, the backward draw runs on the host in sentence order on the engine's
+ *     generator -- a seeded batch reproduces the reference's single-threaded stream bit for bit.
+ * BPE models: alpha <= 0 is the plain Encode; BPE-dropout (alpha > 0, src/bpe_model.cc:132-139) is
+ * not on the accelerated path (SPM_ERR_UNSUPPORTED). */
 int spm_sample_encode_ids(spm_engine *e, const char *bytes, const uint64_t *offsets, size_t n, int nbest_size,
                           float alpha, const int32_t **ids, const uint64_t **id_offsets);
+
+/* Replaces SentencePieceProcessor::CalculateEntropy(input, alpha, &entropy)
+ * (src/sentencepiece_processor.cc:747-760 -> src/unigram_model.cc:266-291,857-864) for n sentences:
+ * entropy[i] of the segmentation lattice of sentence i at inverse temperature alpha (unigram models).
+ * Float results agree with the reference to rounding (the device's expf is not glibc's). */
+int spm_calculate_entropy(spm_engine *e, const char *bytes, const uint64_t *offsets, size_t n, float alpha,
+                          const float **entropy);
+
+/* Replaces SentencePieceProcessor::SampleEncodeAndScore(input, num_samples, alpha, wor, include_best, ...)
+ * (src/sentencepiece_processor.cc:722-745 -> src/unigram_model.cc:741-855) with wor == 0 and
+ * include_best == 0: num_samples independent lattice samples per sentence (one generator, sentence
+ * order, sample order), each with score = sum(alpha * piece score) - log Z.  Sample c of sentence i is
+ * ids[cand_offsets[i*num_samples + c] .. cand_offsets[i*num_samples + c + 1]), score scores[i*num_samples + c].
+ * Sampling without replacement (wor) / include_best are not on the accelerated path. */
+int spm_sample_encode_and_score(spm_engine *e, const char *bytes, const uint64_t *offsets, size_t n, int num_samples,
+                                float alpha, int wor, int include_best, const int32_t **ids,
+                                const uint64_t **cand_offsets, const float **scores);
 
 /* Replaces SentencePieceProcessor::Decode(const std::vector<int>& ids, std::string* detokenized)
  * (src/sentencepiece_processor.cc:911-925 -> :765-909), one call for n id lists: `ids` is the packed

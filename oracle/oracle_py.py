@@ -216,6 +216,40 @@ class OracleModel:
         L.oracle_free(ids)
         return a, ido
 
+    def entropy_batch(self, buf, offs, alpha):
+        """CalculateEntropy per sentence -> float32[n]"""
+        L = self.lib
+        L.oracle_entropy_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
+                                           ctypes.c_float, ctypes.c_void_p]
+        n = len(offs) - 1
+        buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        offs = np.ascontiguousarray(offs, dtype=np.uint64)
+        ent = np.zeros(n, dtype=np.float32)
+        rc = L.oracle_entropy_batch(self.h, buf.ctypes.data, offs.ctypes.data, n, alpha, ent.ctypes.data)
+        if rc:
+            raise RuntimeError(f"oracle_entropy_batch failed ({rc})")
+        return ent
+
+    def sample_score_batch(self, buf, offs, samples, alpha, seed):
+        """SampleEncodeAndScore(wor=False) -> (ids, cand_off uint64[n*samples+1], scores float32[n*samples])"""
+        L = self.lib
+        L.oracle_sample_score_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
+                                                ctypes.c_int, ctypes.c_float, ctypes.c_uint32,
+                                                ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p, ctypes.c_void_p]
+        n = len(offs) - 1
+        buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        offs = np.ascontiguousarray(offs, dtype=np.uint64)
+        co = np.zeros(n * samples + 1, dtype=np.uint64)
+        sc = np.zeros(n * samples, dtype=np.float32)
+        ids = ctypes.c_void_p()
+        rc = L.oracle_sample_score_batch(self.h, buf.ctypes.data, offs.ctypes.data, n, samples, alpha, seed,
+                                         ctypes.byref(ids), co.ctypes.data, sc.ctypes.data)
+        if rc:
+            raise RuntimeError(f"oracle_sample_score_batch failed ({rc})")
+        a = _i32(ids, int(co[-1]))
+        L.oracle_free(ids)
+        return a, co, sc
+
     def encode_batch(self, buf, offs):
         n = len(offs) - 1
         ido = np.zeros(n + 1, dtype=np.uint64)
@@ -380,6 +414,38 @@ class RefModel:
         a = _i32(ids, int(ido[n]))
         L.ref_free_buf(ids)
         return a, ido
+
+    def entropy_batch(self, buf, offs, alpha):
+        L = self.lib
+        L.ref_entropy.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_float,
+                                  ctypes.c_void_p]
+        n = len(offs) - 1
+        buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        offs = np.ascontiguousarray(offs, dtype=np.uint64)
+        ent = np.zeros(n, dtype=np.float32)
+        rc = L.ref_entropy(self.h, buf.ctypes.data, offs.ctypes.data, n, alpha, ent.ctypes.data)
+        if rc:
+            raise RuntimeError(f"reference CalculateEntropy failed at sentence {rc - 1}")
+        return ent
+
+    def sample_score_batch(self, buf, offs, samples, alpha, seed, wor=False, include_best=False):
+        L = self.lib
+        L.ref_sample_score.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int,
+                                       ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_uint,
+                                       ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p, ctypes.c_void_p]
+        n = len(offs) - 1
+        buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        offs = np.ascontiguousarray(offs, dtype=np.uint64)
+        co = np.zeros(n * samples + 1, dtype=np.uint64)
+        sc = np.zeros(n * samples, dtype=np.float32)
+        ids = ctypes.c_void_p()
+        rc = L.ref_sample_score(self.h, buf.ctypes.data, offs.ctypes.data, n, samples, alpha, int(wor), int(include_best),
+                                seed, ctypes.byref(ids), co.ctypes.data, sc.ctypes.data)
+        if rc:
+            raise RuntimeError("reference SampleEncodeAndScore failed")
+        a = _i32(ids, int(co[-1]))
+        self.lib.ref_free_buf(ids)
+        return a, co, sc
 
     def encode_pieces(self, s):
         out = ctypes.c_void_p()

@@ -260,4 +260,46 @@ int ref_sample_encode_ids(void *h, const char *bytes, const uint64_t *offs, size
   return 0;
 }
 
+// CalculateEntropy(input, alpha) per sentence (src/sentencepiece_processor.cc:747-760).
+int ref_entropy(void *h, const char *bytes, const uint64_t *offs, size_t n, float alpha, float *entropy) {
+  auto *sp = static_cast<SentencePieceProcessor *>(h);
+  for (size_t i = 0; i < n; ++i)
+    if (!sp->CalculateEntropy(absl::string_view(bytes + offs[i], offs[i + 1] - offs[i]), alpha, &entropy[i]).ok())
+      return static_cast<int>(i + 1);
+  return 0;
+}
+
+// SampleEncodeAndScore(input, samples, alpha, wor, include_best) over a packed batch, sequentially on a fresh
+// thread (see ref_sample_encode_ids).  Outputs: ids of all samples packed (malloc'ed), cand_off[n*samples+1],
+// scores[n*samples]; a sentence for which the reference returns fewer results leaves empty slots.
+int ref_sample_score(void *h, const char *bytes, const uint64_t *offs, size_t n, int samples, float alpha, int wor,
+                     int include_best, unsigned int seed, int32_t **ids_out, uint64_t *cand_off, float *scores) {
+  auto *sp = static_cast<SentencePieceProcessor *>(h);
+  std::vector<std::vector<std::pair<std::vector<int>, float>>> outs(n);
+  sentencepiece::SetRandomGeneratorSeed(seed);
+  std::thread t([&]() {
+    for (size_t i = 0; i < n; ++i)
+      outs[i] = sp->SampleEncodeAndScoreAsIds(absl::string_view(bytes + offs[i], offs[i + 1] - offs[i]), samples, alpha,
+                                              wor != 0, include_best != 0);
+  });
+  t.join();
+  uint64_t total = 0;
+  size_t c = 0;
+  for (size_t i = 0; i < n; ++i)
+    for (int k = 0; k < samples; ++k, ++c) {
+      cand_off[c] = total;
+      scores[c] = 0.f;
+      if (k < static_cast<int>(outs[i].size())) { total += outs[i][k].first.size(); scores[c] = outs[i][k].second; }
+    }
+  cand_off[c] = total;
+  int32_t *ids = static_cast<int32_t *>(malloc(sizeof(int32_t) * (total ? total : 1)));
+  c = 0;
+  for (size_t i = 0; i < n; ++i)
+    for (int k = 0; k < samples; ++k, ++c)
+      if (k < static_cast<int>(outs[i].size()) && !outs[i][k].first.empty())
+        memcpy(ids + cand_off[c], outs[i][k].first.data(), sizeof(int32_t) * outs[i][k].first.size());
+  *ids_out = ids;
+  return 0;
+}
+
 }  // extern "C"

@@ -996,8 +996,11 @@ int oracle_sample_pick(oracle_mt19937 *g, const float *scores, size_t k, float a
   return (int)lo;
 }
 
+static int sample_lattice_batch(const oracle_model *m, const char *bytes, const uint64_t *offs, size_t n, float alpha,
+                                uint32_t seed, int32_t **ids_out, uint64_t *id_offsets);
 int oracle_sample_encode_batch(const oracle_model *m, const char *bytes, const uint64_t *offs, size_t n, int nbest_size,
                                float alpha, uint32_t seed, int32_t **ids_out, uint64_t *id_offsets) {
+  if (nbest_size < 0) return sample_lattice_batch(m, bytes, offs, n, alpha, seed, ids_out, id_offsets);  /* :689-693 */
   oracle_mt19937 g;
   oracle_mt_seed(&g, seed);
   size_t cap = 1024, total = 0;
@@ -1021,6 +1024,264 @@ int oracle_sample_encode_batch(const oracle_model *m, const char *bytes, const u
   return 0;
 }
 
+
+/* =================================================== full-lattice operations ==
+ * SampleEncode(nbest_size < 0) = forward-filtering / backward-sampling (unigram_model.cc:511-542,
+ * dispatch sentencepiece_processor.cc:689-693), SampleEncodeAndScore with wor == false (:741-855) and
+ * CalculateEntropy (:266-291, :857-864), all over Lattice::ForwardAlgorithm (:200-217) and
+ * LogSumExp (:47-59). */
+typedef struct {
+  int L;                 /* characters */
+  uint32_t *surf;        /* [L+1] byte offset of every character (+ the end) */
+  lnode *nodes;          /* 0 = BOS, 1 = EOS, then PopulateNodes order */
+  size_t nn;
+  ivec *begin_nodes, *end_nodes;  /* [L+1] */
+} lattice_t;
+
+static void lattice_free(lattice_t *t) {
+  for (int i = 0; i <= t->L; ++i) { free(t->begin_nodes[i].a); free(t->end_nodes[i].a); }
+  free(t->begin_nodes); free(t->end_nodes); free(t->nodes); free(t->surf);
+}
+
+/* Lattice::SetSentence (:113-146) + Model::PopulateNodes (:547-596); nlen > 0 */
+static void lattice_build(const oracle_model *m, const unsigned char *norm, size_t nlen, lattice_t *t) {
+  uint32_t *surf = malloc(sizeof(uint32_t) * (nlen + 2));
+  int L = 0;
+  for (size_t p = 0; p < nlen;) {
+    size_t mb = one_char_len(norm[p]);
+    if (mb > nlen - p) mb = nlen - p;
+    surf[L++] = (uint32_t)p;
+    p += mb;
+  }
+  surf[L] = (uint32_t)nlen;
+  size_t ncap = 64, nn = 0;
+  lnode *nodes = malloc(ncap * sizeof(lnode));
+  ivec *begin_nodes = calloc((size_t)L + 1, sizeof(ivec)), *end_nodes = calloc((size_t)L + 1, sizeof(ivec));
+#define NEW_NODE() (nn == ncap ? (nodes = realloc(nodes, (ncap *= 2) * sizeof(lnode)), &nodes[nn++]) : &nodes[nn++])
+  { lnode *bos = NEW_NODE(); memset(bos, 0, sizeof *bos); bos->id = -1; bos->pos = 0; iv_push(&end_nodes[0], 0); }
+  { lnode *eos = NEW_NODE(); memset(eos, 0, sizeof *eos); eos->id = -1; eos->pos = L; iv_push(&begin_nodes[L], 1); }
+  const float unk_score = m->min_score - 10.0f;
+  for (int bp = 0; bp < L; ++bp) {
+    int has_single = 0;
+    uint32_t node = 0;
+    for (size_t kpos = surf[bp]; kpos < nlen; ++kpos) {
+      const int32_t c = ht_child(&m->pieces, node, norm[kpos]);
+      if (c < 0) break;
+      node = (uint32_t)c;
+      const int32_t id = m->pieces.value[node];
+      if (id < 0) continue;
+      const uint32_t endb = (uint32_t)kpos + 1;
+      int length = 0;
+      { int pos = bp; while (surf[pos] < endb) ++pos; length = pos - bp; }
+      if (m->types[id] == ORACLE_UNUSED) continue;
+      lnode *nd = NEW_NODE();
+      memset(nd, 0, sizeof *nd);
+      nd->pos = bp; nd->length = length; nd->id = id;
+      nd->bbeg = surf[bp]; nd->bend = surf[bp + length];
+      nd->score = m->types[id] == ORACLE_USER_DEFINED ? (float)((double)((float)length * m->max_score) - 0.1)
+                                                       : m->scores[id];
+      iv_push(&begin_nodes[bp], (int32_t)(nn - 1));
+      iv_push(&end_nodes[bp + length], (int32_t)(nn - 1));
+      if (!has_single && length == 1) has_single = 1;
+    }
+    if (!has_single) {
+      lnode *nd = NEW_NODE();
+      memset(nd, 0, sizeof *nd);
+      nd->pos = bp; nd->length = 1; nd->id = m->unk_id; nd->score = unk_score;
+      nd->bbeg = surf[bp]; nd->bend = surf[bp + 1];
+      iv_push(&begin_nodes[bp], (int32_t)(nn - 1));
+      iv_push(&end_nodes[bp + 1], (int32_t)(nn - 1));
+    }
+  }
+#undef NEW_NODE
+  t->L = L; t->surf = surf; t->nodes = nodes; t->nn = nn; t->begin_nodes = begin_nodes; t->end_nodes = end_nodes;
+}
+
+/* unigram_model.cc:47-59 */
+static float log_sum_exp(float x, float y, int init_mode) {
+  if (init_mode) return y;
+  const float vmin = x < y ? x : y;   /* std::min / std::max */
+  const float vmax = x < y ? y : x;
+  if (vmax > vmin + 50.f) return vmax;
+  return (float)(vmax + log(exp((double)(vmin - vmax)) + 1.0));
+}
+
+/* Lattice::ForwardAlgorithm, :200-217; alpha is indexed by node */
+static float *lattice_forward(const lattice_t *t, float inv_theta) {
+  float *alpha = calloc(t->nn, sizeof(float));
+  for (int pos = 0; pos <= t->L; ++pos)
+    for (size_t r = 0; r < t->begin_nodes[pos].n; ++r) {
+      const int32_t rn = t->begin_nodes[pos].a[r];
+      for (size_t q = 0; q < t->end_nodes[pos].n; ++q) {
+        const int32_t ln = t->end_nodes[pos].a[q];
+        const float prod = inv_theta * t->nodes[ln].score;   /* float product, then float sum */
+        alpha[rn] = log_sum_exp(alpha[rn], prod + alpha[ln], q == 0);
+      }
+    }
+  return alpha;
+}
+
+/* libstdc++ std::discrete_distribution<int>(probs.begin(), probs.end()) + operator()(mt) on float probabilities */
+static int discrete_pick(oracle_mt19937 *g, const float *probs, size_t k) {
+  if (k < 2) return 0;
+  double *cp = malloc(sizeof(double) * k);
+  double sum = 0.0;
+  for (size_t i = 0; i < k; ++i) sum += (double)probs[i];
+  double run = 0.0;
+  for (size_t i = 0; i < k; ++i) { run += (double)probs[i] / sum; cp[i] = run; }
+  cp[k - 1] = 1.0;
+  const double x0 = (double)mt_next(g), x1 = (double)mt_next(g);
+  double p = (x0 + x1 * 4294967296.0) / 18446744073709551616.0;
+  if (p >= 1.0) p = nextafter(1.0, 0.0);
+  size_t lo = 0, hi = k;
+  while (lo < hi) { const size_t mid = lo + (hi - lo) / 2; if (cp[mid] < p) lo = mid + 1; else hi = mid; }
+  free(cp);
+  return (int)lo;
+}
+
+/* Lattice::Sample, :511-542: node indices of the sampled path, left to right; returns the count */
+static size_t lattice_sample(const lattice_t *t, const float *alpha, float inv_theta, oracle_mt19937 *g, int32_t *path) {
+  size_t np = 0, pcap = 16;
+  float *probs = malloc(sizeof(float) * pcap);
+  float Z = alpha[1];
+  int32_t node = 1;  /* EOS */
+  for (;;) {
+    const ivec *en = &t->end_nodes[t->nodes[node].pos];
+    if (en->n > pcap) { pcap = en->n; probs = realloc(probs, sizeof(float) * pcap); }
+    for (size_t q = 0; q < en->n; ++q) {
+      const lnode *ln = &t->nodes[en->a[q]];
+      const float prod = inv_theta * ln->score;
+      const float arg = alpha[en->a[q]] + prod - Z;          /* float expression, widened for exp */
+      probs[q] = (float)exp((double)arg);                     /* std::vector<float> probs */
+    }
+    node = en->a[discrete_pick(g, probs, en->n)];
+    if (node == 0) break;
+    Z = alpha[node];
+    path[np++] = node;
+  }
+  free(probs);
+  for (size_t i = 0; i < np / 2; ++i) { const int32_t x = path[i]; path[i] = path[np - 1 - i]; path[np - 1 - i] = x; }
+  return np;
+}
+
+static void emit_path(const oracle_model *m, const unsigned char *norm, const lattice_t *t, const int32_t *path, size_t np,
+                      outv *o) {
+  uint32_t *pl = malloc(sizeof(uint32_t) * (np ? np : 1));
+  int32_t *pi = malloc(sizeof(int32_t) * (np ? np : 1));
+  for (size_t i = 0; i < np; ++i) {
+    pl[i] = t->nodes[path[i]].bend - t->nodes[path[i]].bbeg;
+    pi[i] = t->nodes[path[i]].id;
+  }
+  emit_candidate(m, norm, pl, pi, np, o);
+  free(pl); free(pi);
+}
+
+/* SampleEncode(input, nbest_size < 0, alpha) over a packed batch in order on one generator. */
+static int sample_lattice_batch(const oracle_model *m, const char *bytes, const uint64_t *offs, size_t n, float alpha,
+                                uint32_t seed, int32_t **ids_out, uint64_t *id_offsets) {
+  if (m->model_type != ORACLE_UNIGRAM) return -1;
+  oracle_mt19937 g;
+  oracle_mt_seed(&g, seed);
+  outv all = {0};
+  for (size_t i = 0; i < n; ++i) {
+    char *norm_; size_t nlen; uint64_t *n2o; size_t n2o_len;
+    id_offsets[i] = all.n;
+    if (oracle_normalize(m, bytes + offs[i], (size_t)(offs[i + 1] - offs[i]), &norm_, &nlen, &n2o, &n2o_len)) { free(all.ids); free(all.ends); return (int)(i + 1); }
+    free(n2o);
+    if (nlen) {
+      lattice_t t;
+      lattice_build(m, (const unsigned char *)norm_, nlen, &t);
+      float *a = lattice_forward(&t, alpha);
+      int32_t *path = malloc(sizeof(int32_t) * ((size_t)t.L + 1));
+      const size_t np = lattice_sample(&t, a, alpha, &g, path);
+      emit_path(m, (const unsigned char *)norm_, &t, path, np, &all);
+      free(path); free(a);
+      lattice_free(&t);
+    }
+    free(norm_);
+  }
+  id_offsets[n] = all.n;
+  free(all.ends);
+  *ids_out = all.ids ? all.ids : malloc(4);
+  return 0;
+}
+
+/* SentencePieceProcessor::CalculateEntropy (sentencepiece_processor.cc:747-760 -> unigram_model.cc:266-291,857-864) */
+int oracle_entropy_batch(const oracle_model *m, const char *bytes, const uint64_t *offs, size_t n, float inv_theta,
+                         float *entropy) {
+  if (m->model_type != ORACLE_UNIGRAM) return -1;
+  for (size_t i = 0; i < n; ++i) {
+    char *norm_; size_t nlen; uint64_t *n2o; size_t n2o_len;
+    if (oracle_normalize(m, bytes + offs[i], (size_t)(offs[i + 1] - offs[i]), &norm_, &nlen, &n2o, &n2o_len)) return (int)(i + 1);
+    free(n2o);
+    entropy[i] = -0.0f;  /* an empty lattice: H[EOS] = 0, returned negated */
+    if (nlen) {
+      lattice_t t;
+      lattice_build(m, (const unsigned char *)norm_, nlen, &t);
+      float *a = lattice_forward(&t, inv_theta);
+      float *H = calloc(t.nn, sizeof(float));
+      for (int pos = 0; pos <= t.L; ++pos)
+        for (size_t r = 0; r < t.begin_nodes[pos].n; ++r) {
+          const int32_t rn = t.begin_nodes[pos].a[r];
+          for (size_t q = 0; q < t.end_nodes[pos].n; ++q) {
+            const int32_t ln = t.end_nodes[pos].a[q];
+            const float prod = inv_theta * t.nodes[ln].score;
+            const float tp = prod + a[ln] - a[rn];
+            H[rn] += expf(tp) * (H[ln] + tp);                 /* std::exp(float) */
+          }
+        }
+      entropy[i] = -H[1];
+      free(H); free(a);
+      lattice_free(&t);
+    }
+    free(norm_);
+  }
+  return 0;
+}
+
+/* SampleEncodeAndScore(input, samples, alpha, wor = false, include_best = false) over a packed batch in order on
+ * one generator (unigram_model.cc:741-855): `samples` independent Lattice::Sample draws per sentence, each scored
+ * sum(alpha * node score) - log Z.  Outputs: ids of all samples packed, cand_off[n*samples+1], scores[n*samples]. */
+int oracle_sample_score_batch(const oracle_model *m, const char *bytes, const uint64_t *offs, size_t n, int samples,
+                              float inv_theta, uint32_t seed, int32_t **ids_out, uint64_t *cand_off, float *scores) {
+  if (m->model_type != ORACLE_UNIGRAM || samples < 1) return -1;
+  oracle_mt19937 g;
+  oracle_mt_seed(&g, seed);
+  outv all = {0};
+  size_t c = 0;
+  for (size_t i = 0; i < n; ++i) {
+    char *norm_; size_t nlen; uint64_t *n2o; size_t n2o_len;
+    if (oracle_normalize(m, bytes + offs[i], (size_t)(offs[i + 1] - offs[i]), &norm_, &nlen, &n2o, &n2o_len)) { free(all.ids); free(all.ends); return (int)(i + 1); }
+    free(n2o);
+    if (!nlen) {  /* the reference returns no result at all ("SampleEncodeAndScore returns empty result."): empty slots */
+      for (int k = 0; k < samples; ++k) { cand_off[c] = all.n; scores[c] = 0.f; ++c; }
+      free(norm_);
+      continue;
+    }
+    lattice_t t;
+    lattice_build(m, (const unsigned char *)norm_, nlen, &t);
+    float *a = lattice_forward(&t, inv_theta);
+    const float marginal = a[1];
+    int32_t *path = malloc(sizeof(int32_t) * ((size_t)t.L + 1));
+    for (int k = 0; k < samples; ++k) {
+      /* every draw rebuilds the lattice and its alpha in the reference (:838-851); same values */
+      const size_t np = lattice_sample(&t, a, inv_theta, &g, path);
+      float score = 0.f;
+      for (size_t j = 0; j < np; ++j) score += inv_theta * t.nodes[path[j]].score;
+      cand_off[c] = all.n;
+      emit_path(m, (const unsigned char *)norm_, &t, path, np, &all);
+      scores[c] = score - marginal;
+      ++c;
+    }
+    free(path); free(a);
+    lattice_free(&t);
+    free(norm_);
+  }
+  cand_off[c] = all.n;
+  free(all.ends);
+  *ids_out = all.ids ? all.ids : malloc(4);
+  return 0;
+}
 
 /* ------------------------------------------------------------------------------------------------
  * SentencePieceProcessor::Decode(const std::vector<int>&, SentencePieceText*) -- text only

@@ -95,6 +95,17 @@ int oracle_sample_pick(oracle_mt19937 *g, const float *scores, size_t k, float a
 int oracle_sample_encode_batch(const oracle_model *m, const char *bytes, const uint64_t *offs, size_t n, int nbest_size,
                                float alpha, uint32_t seed, int32_t **ids, uint64_t *id_offsets);
 
+/* ---- next row: full-lattice operations of unigram models.
+ * oracle_sample_encode_batch with nbest_size < 0 is SampleEncode's forward-filtering / backward-sampling branch
+ * (sentencepiece_processor.cc:689-693 -> unigram_model.cc:511-542).  CalculateEntropy per sentence
+ * (sentencepiece_processor.cc:747-760 -> unigram_model.cc:266-291) and SampleEncodeAndScore(wor = false,
+ * include_best = false) (unigram_model.cc:741-855): `samples` draws per sentence on one generator across the batch,
+ * candidate c of sentence i = ids[cand_off[i*samples+c] .. cand_off[i*samples+c+1]) with score scores[i*samples+c]. */
+int oracle_entropy_batch(const oracle_model *m, const char *bytes, const uint64_t *offs, size_t n, float inv_theta,
+                         float *entropy);
+int oracle_sample_score_batch(const oracle_model *m, const char *bytes, const uint64_t *offs, size_t n, int samples,
+                              float inv_theta, uint32_t seed, int32_t **ids, uint64_t *cand_off, float *scores);
+
 /* ---- next row: SentencePieceProcessor::Decode(ids) -> text
  * (src/sentencepiece_processor.cc:765-925): IdToPiece, CONTROL pieces invisible, UNKNOWN -> unk_surface, the first
  * U+2581 stripped while the text is still empty (add_dummy_prefix / remove_extra_whitespaces), U+2581 -> ' ', runs of

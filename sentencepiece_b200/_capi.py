@@ -14,7 +14,8 @@ EXPORTS = [
     "spm_engine_create", "spm_engine_create_from_serialized", "spm_engine_destroy", "spm_engine_set_types",
     "spm_last_error", "spm_encode_ids", "spm_encode_spans", "spm_encode_ids_device", "spm_host_alloc",
     "spm_host_free", "spm_engine_get_info", "spm_engine_set_tuning", "spm_nbest_encode", "spm_set_random_seed",
-    "spm_sample_encode_ids", "spm_decode_ids", "spm_engine_set_unk_surface",
+    "spm_sample_encode_ids", "spm_decode_ids", "spm_engine_set_unk_surface", "spm_calculate_entropy",
+    "spm_sample_encode_and_score",
 ]
 
 
@@ -74,5 +75,8 @@ def load():
     L.spm_sample_encode_ids.argtypes = [vp, vp, vp, sz, ctypes.c_int, ctypes.c_float, P(vp), P(vp)]
     L.spm_decode_ids.argtypes = [vp, vp, vp, sz, P(vp), P(vp)]
     L.spm_engine_set_unk_surface.argtypes = [vp, cp, sz]
+    L.spm_calculate_entropy.argtypes = [vp, vp, vp, sz, ctypes.c_float, P(vp)]
+    L.spm_sample_encode_and_score.argtypes = [vp, vp, vp, sz, ctypes.c_int, ctypes.c_float, ctypes.c_int, ctypes.c_int,
+                                              P(vp), P(vp), P(vp)]
     _lib = L
     return L

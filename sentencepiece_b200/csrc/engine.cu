@@ -36,6 +36,7 @@
 #include "order_kernel.cuh"
 #include "decode_kernel.cuh"
 #include "nbest_kernel.cuh"
+#include "lattice_kernel.cuh"
 #include "trie_builder.h"
 #include "unigram_warp.cuh"
 
@@ -251,6 +252,24 @@ struct spm_engine {
   PinBuf<uint32_t> h_n_cands, h_picks;
   PinBuf<uint64_t> h_cand_offsets;
   std::mt19937 rng{5489u};
+  // full-lattice operations (lattice_kernel.cuh): exported lattices of one chunk of sentences
+  DevBuf<uint8_t> d_lat_scratch;
+  DevBuf<uint4> d_lat_nodes;
+  DevBuf<uint2> d_lat_pos;
+  DevBuf<unsigned long long> d_lat_node_start, d_lat_pos_start;
+  DevBuf<uint32_t> d_lat_nchars;
+  DevBuf<float> d_lat_entropy;
+  PinBuf<uint4> h_lat_nodes;
+  PinBuf<uint2> h_lat_pos;
+  PinBuf<unsigned long long> h_lat_node_start, h_lat_pos_start;
+  PinBuf<uint32_t> h_lat_nchars;
+  PinBuf<float> h_lat_entropy;
+  std::vector<int32_t> byte_to_id_host;
+  std::vector<int32_t> lat_ids;          // results of the last lattice sampling call
+  std::vector<uint64_t> lat_offsets;
+  std::vector<float> lat_scores;
+  // mode 0: samples >= 1 draws per sentence from the lattice (ids, offsets[n*samples+1], scores); mode 1: entropy
+  int run_lattice(const char *bytes, const uint64_t *offsets, size_t n, float inv_theta, int mode, int samples);
   int run_nbest(const char *bytes, const uint64_t *offsets, size_t n, uint32_t nbest, uint64_t *tmp_total);
 
   // stats of the last call
@@ -445,6 +464,7 @@ int spm_engine::build_tables() {
   CUDA_TRY(d_cm_pair.upload(cm_pair));
   CUDA_TRY(d_cm_solo.upload(cm_solo));
   CUDA_TRY(d_byte_to_id.upload(byte_to_id));
+  byte_to_id_host = byte_to_id;
   CUDA_TRY(d_scores.upload(m.scores));
   CUDA_TRY(d_types.upload(m.types));
 
@@ -693,6 +713,7 @@ int spm_engine::configure_kernel_attrs() {
   CUDA_TRY(set_smem(encode_bpe_lane_kernel, mx));
   CUDA_TRY(set_smem(encode_bpe_lane2_kernel, mx));
   CUDA_TRY(set_smem(nbest_lane_kernel<kNbestTop, 1024>, mx));
+  CUDA_TRY(set_smem(lattice_lane_kernel, mx));
   CUDA_TRY(set_smem(encode_unigram_warp_kernel<512>, mx));
   CUDA_TRY(set_smem(encode_unigram_warp_kernel<1024>, mx));
   CUDA_TRY(set_smem(encode_bpe_kernel<false>, mx));
@@ -1585,6 +1606,177 @@ int spm_engine::run_nbest(const char *bytes, const uint64_t *offsets, size_t n, 
   return SPM_ERR_CAPACITY;
 }
 
+// ---- full-lattice operations: lattice + forward algorithm on the GPU (lattice_kernel.cuh), in
+//      chunks of sentences; mode 0 then draws on the host exactly as Lattice::Sample (unigram_model.cc:511-542) does
+//      -- std::exp in double, std::discrete_distribution<int> over float probabilities, this engine's std::mt19937 --
+//      for the sentences in order, which reproduces the reference's single-threaded stream under a seed ----
+int spm_engine::run_lattice(const char *bytes, const uint64_t *offsets, size_t n, float inv_theta, int mode, int samples) {
+  cudaStream_t st = stream;
+  lat_ids.clear();
+  lat_scores.clear();
+  lat_offsets.assign(1, 0);
+  CUDA_TRY(d_ctrl32.ensure(16));
+  CUDA_TRY(d_ctrl64.ensure(4));
+  CUDA_TRY(h_ctrl32.ensure(16));
+  CUDA_TRY(h_ctrl64.ensure(4));
+  LatticeGeom G{};
+  G.cap = lane_cap;
+  G.node_cap = lane_cap * (trie.max_matches_per_start + 1) + 64;
+  constexpr size_t kChunk = 32768;
+  const int warps_per_cta = 8;
+  last_launches = 0;
+  last_h2d = last_d2h = 0;
+  float main_ms = 0.f;
+  if (mode == 1) CUDA_TRY(h_lat_entropy.ensure(n + 1));
+  std::vector<float> probs;
+  std::vector<uint32_t> path;
+  for (size_t lo = 0; lo < n; lo += kChunk) {
+    const size_t m = std::min(kChunk, n - lo);
+    const uint64_t base = offsets[lo];
+    const uint64_t chunk_bytes = offsets[lo + m] - base;
+    CUDA_TRY(d_bytes.ensure(chunk_bytes + 64));
+    CUDA_TRY(d_offsets.ensure(m + 1));
+    if (chunk_bytes) CUDA_TRY(cudaMemcpyAsync(d_bytes.p, bytes + base, chunk_bytes, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_offsets.p, offsets + lo, (m + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    last_h2d += chunk_bytes + (m + 1) * sizeof(uint64_t);
+    const size_t groups = (m + 31) / 32;
+    const int ctas = static_cast<int>(std::min<size_t>(sm_count, (groups + warps_per_cta - 1) / warps_per_cta));
+    const size_t warps_total = static_cast<size_t>(ctas) * warps_per_cta;
+    CUDA_TRY(d_lane_slabs.ensure(warps_total * lane_slab_bytes(lane_cap) + 256));
+    CUDA_TRY(d_lat_scratch.ensure(warps_total * 32 * lattice_lane_bytes(G) + 256));
+    CUDA_TRY(d_lat_node_start.ensure(m));
+    CUDA_TRY(d_lat_pos_start.ensure(m));
+    CUDA_TRY(d_lat_nchars.ensure(m));
+    CUDA_TRY(d_lat_entropy.ensure(m));
+    // a sentence of b normalized bytes has at most b + 2 position records; nodes: start from 3 per input byte
+    unsigned long long node_cap = mode == 0 ? 3ull * chunk_bytes + 64ull * m + 1024 : 1;
+    const unsigned long long pos_cap = mode == 0 ? (chunk_bytes * max_expand_num) / max_expand_den + 16ull * m + 1024 : 1;
+    for (int attempt = 0;; ++attempt) {
+      CUDA_TRY(d_lat_nodes.ensure(node_cap));
+      CUDA_TRY(d_lat_pos.ensure(pos_cap));
+      CUDA_TRY(cudaMemsetAsync(d_ctrl32.p, 0, 16 * sizeof(uint32_t), st));
+      CUDA_TRY(cudaMemsetAsync(d_ctrl64.p, 0, 4 * sizeof(unsigned long long), st));
+      KBatch B{};
+      B.bytes = d_bytes.p - base;
+      B.offsets = d_offsets.p;
+      B.n = static_cast<uint32_t>(m);
+      B.off_lo = 0;
+      B.off_hi = ~0ull;
+      B.work_counter = d_ctrl32.p + 4;
+      B.status = d_ctrl32.p;
+      LatticeOut O{};
+      O.nodes = d_lat_nodes.p;
+      O.pos = d_lat_pos.p;
+      O.node_cap = node_cap;
+      O.pos_cap = pos_cap;
+      O.cursor = d_ctrl64.p;
+      O.node_start = d_lat_node_start.p;
+      O.pos_start = d_lat_pos_start.p;
+      O.n_chars = d_lat_nchars.p;
+      O.entropy = d_lat_entropy.p;
+      O.status = d_ctrl32.p;
+      CUDA_TRY(cudaEventRecord(ev[0], st));
+      lattice_lane_kernel<<<ctas, warps_per_cta * 32, kLaneTableBytes, st>>>(km, B, O, d_lane_slabs.p, d_lat_scratch.p, G,
+                                                                            inv_theta, mode);
+      CUDA_TRY(cudaGetLastError());
+      CUDA_TRY(cudaEventRecord(ev[1], st));
+      ++last_launches;
+      CUDA_TRY(cudaMemcpyAsync(h_ctrl32.p, d_ctrl32.p, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaMemcpyAsync(h_ctrl64.p, d_ctrl64.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaStreamSynchronize(st));
+      float a = 0.f;
+      if (cudaEventElapsedTime(&a, ev[0], ev[1]) == cudaSuccess) main_ms += a;
+      if (h_ctrl32.p[3]) {
+        set_error("lattice: a sentence exceeds the device path's capacity (normalized length > " + std::to_string(lane_cap) + " bytes)");
+        return SPM_ERR_UNSUPPORTED;
+      }
+      if (h_ctrl32.p[2] && attempt == 0) { node_cap = h_ctrl64.p[0] + 1024; continue; }
+      if (h_ctrl32.p[2]) { set_error("lattice: output buffer overflow persisted"); return SPM_ERR_CAPACITY; }
+      break;
+    }
+    if (mode == 1) {
+      CUDA_TRY(cudaMemcpyAsync(h_lat_entropy.p + lo, d_lat_entropy.p, m * sizeof(float), cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaStreamSynchronize(st));
+      last_d2h += m * sizeof(float);
+      continue;
+    }
+    const unsigned long long tot_nodes = h_ctrl64.p[0], tot_pos = h_ctrl64.p[1];
+    CUDA_TRY(h_lat_nodes.ensure(tot_nodes + 1));
+    CUDA_TRY(h_lat_pos.ensure(tot_pos + 1));
+    CUDA_TRY(h_lat_node_start.ensure(m));
+    CUDA_TRY(h_lat_pos_start.ensure(m));
+    CUDA_TRY(h_lat_nchars.ensure(m));
+    if (tot_nodes) CUDA_TRY(cudaMemcpyAsync(h_lat_nodes.p, d_lat_nodes.p, tot_nodes * sizeof(uint4), cudaMemcpyDeviceToHost, st));
+    if (tot_pos) CUDA_TRY(cudaMemcpyAsync(h_lat_pos.p, d_lat_pos.p, tot_pos * sizeof(uint2), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(h_lat_node_start.p, d_lat_node_start.p, m * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(h_lat_pos_start.p, d_lat_pos_start.p, m * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(h_lat_nchars.p, d_lat_nchars.p, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    last_d2h += tot_nodes * sizeof(uint4) + tot_pos * sizeof(uint2) + m * 20;
+    // ---- Lattice::Sample per sentence, in order, on one generator ----
+    const bool bf = model.byte_fallback;
+    for (size_t i = 0; i < m; ++i) {
+      const uint32_t L = h_lat_nchars.p[i];
+      const uint4 *nodes = h_lat_nodes.p + h_lat_node_start.p[i];
+      const uint2 *pos = h_lat_pos.p + h_lat_pos_start.p[i];
+      for (int sidx = 0; sidx < samples; ++sidx) {
+        float score = 0.f;
+        if (L) {
+          auto A = [&](uint32_t p) { float f; memcpy(&f, &pos[p].x, 4); return f; };
+          path.clear();
+          float Z = A(L);
+          uint32_t p = L;
+          while (p != 0) {  // at position 0 the only candidate is BOS: no draw (a one-weight distribution)
+            const uint32_t q0 = pos[p].y, q1 = pos[p + 1].y;
+            probs.clear();
+            for (uint32_t q = q0; q < q1; ++q) {
+              float sc; memcpy(&sc, &nodes[q].y, 4);
+              const float arg = A(nodes[q].z & 0xFFFFu) + inv_theta * sc - Z;   // float expression (:528-529)
+              probs.push_back(static_cast<float>(std::exp(static_cast<double>(arg))));
+            }
+            std::discrete_distribution<int> dist(probs.begin(), probs.end());
+            const uint32_t q = q0 + static_cast<uint32_t>(dist(rng));
+            path.push_back(q);
+            p = nodes[q].z & 0xFFFFu;
+            Z = A(p);
+          }
+          // id path of PopulateSentencePieceText over the sampled nodes, left to right
+          bool prev_unk = false;
+          for (size_t k = path.size(); k-- > 0;) {
+            const uint4 nd = nodes[path[k]];
+            float sc; memcpy(&sc, &nd.y, 4);
+            score += inv_theta * sc;   // (:846-847)
+            const int32_t id = static_cast<int32_t>(nd.x);
+            const bool isunk = id == unk_id;
+            if (isunk && bf) {
+              const uint32_t first = nd.w & 0xFFu;
+              static const uint8_t kLen[16] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 2, 2, 3, 4};
+              uint32_t cl = kLen[first >> 4];
+              // the node covers one character of the normalized text; its byte count is the span of the character
+              // (a truncated character at the end of the text has fewer bytes: the bytes above it are zero and a
+              //  zero byte never follows a multi-byte lead in normalized text)
+              for (uint32_t bq = 0; bq < cl; ++bq) {
+                const uint32_t bv = (nd.w >> (8 * bq)) & 0xFFu;
+                if (bq > 0 && bv == 0) break;
+                lat_ids.push_back(byte_to_id_host[bv]);
+              }
+            } else if (!(isunk && prev_unk)) {
+              lat_ids.push_back(id);
+            }
+            prev_unk = isunk;
+          }
+          score -= A(L);  // - marginal (:853)
+        }
+        lat_offsets.push_back(lat_ids.size());
+        lat_scores.push_back(score);
+      }
+    }
+  }
+  last_main_ms = main_ms;
+  last_ms = main_ms;
+  return SPM_OK;
+}
+
 // ---------------------------------------------------------------- C ABI ----
 
 extern "C" {
@@ -1682,6 +1874,10 @@ void spm_engine_destroy(spm_engine *e) {
   e->d_long_off.release();
   e->d_lane_slabs.release();
   e->d_node2.release();
+  e->d_lat_scratch.release(); e->d_lat_nodes.release(); e->d_lat_pos.release(); e->d_lat_node_start.release();
+  e->d_lat_pos_start.release(); e->d_lat_nchars.release(); e->d_lat_entropy.release(); e->h_lat_nodes.release();
+  e->h_lat_pos.release(); e->h_lat_node_start.release(); e->h_lat_pos_start.release(); e->h_lat_nchars.release();
+  e->h_lat_entropy.release();
   e->d_nb_scratch.release(); e->d_cand_start.release(); e->d_cand_offsets.release(); e->d_cand_count.release();
   e->d_n_cands.release(); e->d_picks.release(); e->d_cand_score.release(); e->h_cand_score.release();
   e->h_n_cands.release(); e->h_picks.release(); e->h_cand_offsets.release();
@@ -1923,11 +2119,9 @@ int spm_encode_ids_device(spm_engine *e, const char *d_bytes, const uint64_t *d_
   return SPM_OK;
 }
 
-static int encode_host(spm_engine *e, const char *bytes, const uint64_t *offsets, size_t n, bool spans,
-                       const int32_t **ids, const uint32_t **tok_end, const uint64_t **id_offsets,
-                       const char **normalized, const uint64_t **norm_offsets, const uint32_t **n2o) {
-  if (!e) return SPM_ERR_ARG;
-  std::lock_guard<std::mutex> lk(e->mu);
+static int encode_host_locked(spm_engine *e, const char *bytes, const uint64_t *offsets, size_t n, bool spans,
+                              const int32_t **ids, const uint32_t **tok_end, const uint64_t **id_offsets,
+                              const char **normalized, const uint64_t **norm_offsets, const uint32_t **n2o) {
   auto set_error = [&](const std::string &m) { e->set_error(m); };
   if (!offsets || !ids || !id_offsets || (n && !bytes && offsets[n] != offsets[0])) { e->set_error("null argument"); return SPM_ERR_ARG; }
   if (n >= 0xFFFFFFF0ull) { e->set_error("too many sentences in one call"); return SPM_ERR_ARG; }
@@ -1987,10 +2181,14 @@ static int encode_host(spm_engine *e, const char *bytes, const uint64_t *offsets
   return SPM_OK;
 }
 
-int spm_encode_ids(spm_engine *e, const char *bytes, const uint64_t *offsets, size_t n, const int32_t **ids,
-                   const uint64_t **id_offsets) {
-  if (e && offsets && ids && id_offsets && bytes && n >= e->pipeline_min_sentences && n < 0xFFFFFFF0ull) {
-    std::lock_guard<std::mutex> lk(e->mu);
+static int encode_host_locked(spm_engine *e, const char *bytes, const uint64_t *offsets, size_t n, bool spans,
+                              const int32_t **ids, const uint32_t **tok_end, const uint64_t **id_offsets,
+                              const char **normalized, const uint64_t **norm_offsets, const uint32_t **n2o);
+
+// spm_encode_ids with e->mu already held (also used by the n-best / sampling entry points for nbest_size <= 1)
+static int encode_ids_locked(spm_engine *e, const char *bytes, const uint64_t *offsets, size_t n, const int32_t **ids,
+                             const uint64_t **id_offsets) {
+  if (offsets && ids && id_offsets && bytes && n >= e->pipeline_min_sentences && n < 0xFFFFFFF0ull) {
     if (e->uses_lane_kernel() && e->sort_by_length && e->fused_host_path) {
       if (e->fused_skip > 0) --e->fused_skip;
       else return e->encode_host_fused(bytes, offsets, n, ids, id_offsets);
@@ -1998,7 +2196,14 @@ int spm_encode_ids(spm_engine *e, const char *bytes, const uint64_t *offsets, si
     if (e->uses_lane_kernel()) return e->encode_host_streamed(bytes, offsets, n, ids, id_offsets);
     return e->encode_host_pipelined(bytes, offsets, n, ids, id_offsets);
   }
-  return encode_host(e, bytes, offsets, n, false, ids, nullptr, id_offsets, nullptr, nullptr, nullptr);
+  return encode_host_locked(e, bytes, offsets, n, false, ids, nullptr, id_offsets, nullptr, nullptr, nullptr);
+}
+
+int spm_encode_ids(spm_engine *e, const char *bytes, const uint64_t *offsets, size_t n, const int32_t **ids,
+                   const uint64_t **id_offsets) {
+  if (!e) return SPM_ERR_ARG;
+  std::lock_guard<std::mutex> lk(e->mu);
+  return encode_ids_locked(e, bytes, offsets, n, ids, id_offsets);
 }
 
 static int nbest_args_ok(spm_engine *e, const char *bytes, const uint64_t *offsets, size_t n) {
@@ -2030,6 +2235,7 @@ int spm_nbest_encode(spm_engine *e, const char *bytes, const uint64_t *offsets, 
   const uint32_t K = static_cast<uint32_t>(std::max(1, std::min(nbest_size, 1024)));  // unigram_model.cc:701
   cudaStream_t st = e->stream;
   const size_t nc = n * static_cast<size_t>(K);
+  if (nc >= 0xFFFFFFF0ull) { e->set_error("n-best: sentences x nbest_size must stay below 2^32; split the batch"); return SPM_ERR_ARG; }
   CUDA_TRY(e->h_cand_offsets.ensure(nc + 1));
   CUDA_TRY(e->h_cand_score.ensure(nc + 1));
   CUDA_TRY(e->h_n_cands.ensure(n + 1));
@@ -2041,9 +2247,7 @@ int spm_nbest_encode(spm_engine *e, const char *bytes, const uint64_t *offsets, 
   if (K == 1) {
     // nbest_size <= 1: {Encode(normalized), 0.0} (unigram_model.cc:703-705)
     const int32_t *pid; const uint64_t *poff;
-    e->mu.unlock();
-    const int rc = spm_encode_ids(e, bytes, offsets, n, &pid, &poff);
-    e->mu.lock();
+    const int rc = encode_ids_locked(e, bytes, offsets, n, &pid, &poff);
     if (rc) return rc;
     for (size_t i = 0; i <= n; ++i) e->h_cand_offsets.p[i] = poff[i];
     for (size_t i = 0; i < n; ++i) { e->h_cand_score.p[i] = 0.f; e->h_n_cands.p[i] = 1; }
@@ -2081,13 +2285,29 @@ int spm_nbest_encode(spm_engine *e, const char *bytes, const uint64_t *offsets, 
 int spm_sample_encode_ids(spm_engine *e, const char *bytes, const uint64_t *offsets, size_t n, int nbest_size,
                           float alpha, const int32_t **ids, const uint64_t **id_offsets) {
   if (!e || !ids || !id_offsets) return SPM_ERR_ARG;
-  if (nbest_size > 512) { e->set_error("nbest_size must be nbest_size <= 512"); return SPM_ERR_ARG; }  // :683
-  if (nbest_size < 0) {
-    e->set_error("SampleEncode with nbest_size < 0 (forward-filtering/backward-sampling) is not on the accelerated path");
-    return SPM_ERR_UNSUPPORTED;
-  }
-  if (nbest_size <= 1) return spm_encode_ids(e, bytes, offsets, n, ids, id_offsets);  // :695-698
   std::lock_guard<std::mutex> lk(e->mu);
+  if (nbest_size > 512) { e->set_error("nbest_size must be nbest_size <= 512"); return SPM_ERR_ARG; }  // :683
+  if (e->model.model_type != SPM_UNIGRAM) {
+    // models without NBestEncode go to Model::SampleEncode(normalized, alpha) whatever nbest_size is (:689-693): for
+    // BPE that is BPE-dropout, which equals Encode only for alpha <= 0 (bpe_model.cc:132-139)
+    if (alpha > 0.f) {
+      e->set_error("SampleEncode: BPE-dropout (alpha > 0) is not on the accelerated path");
+      return SPM_ERR_UNSUPPORTED;
+    }
+    return encode_ids_locked(e, bytes, offsets, n, ids, id_offsets);
+  }
+  if (nbest_size < 0) {
+    // forward-filtering / backward-sampling over the whole lattice (unigram_model.cc:511-542)
+    { const int rc = nbest_args_ok(e, bytes, offsets, n); if (rc) return rc; }
+    if (cudaSetDevice(e->device) != cudaSuccess) { e->set_error("cudaSetDevice failed"); return SPM_ERR_CUDA; }
+    const int rc = e->run_lattice(bytes, offsets, n, alpha, 0, 1);
+    if (rc) return rc;
+    if (e->lat_ids.empty()) e->lat_ids.reserve(1);
+    *ids = e->lat_ids.data();
+    *id_offsets = e->lat_offsets.data();
+    return SPM_OK;
+  }
+  if (nbest_size <= 1) return encode_ids_locked(e, bytes, offsets, n, ids, id_offsets);  // :695-698
   auto set_error = [&](const std::string &m) { e->set_error(m); };
   { const int rc = nbest_args_ok(e, bytes, offsets, n); if (rc) return rc; }
   CUDA_TRY(cudaSetDevice(e->device));
@@ -2182,11 +2402,55 @@ int spm_sample_encode_ids(spm_engine *e, const char *bytes, const uint64_t *offs
   return SPM_OK;
 }
 
+int spm_calculate_entropy(spm_engine *e, const char *bytes, const uint64_t *offsets, size_t n, float alpha,
+                          const float **entropy) {
+  if (!e || !entropy) return SPM_ERR_ARG;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (e->model.model_type != SPM_UNIGRAM) {
+    e->set_error("CalculateEntropy is not available for the current model.");  // sentencepiece_processor.cc:750-751
+    return SPM_ERR_UNSUPPORTED;
+  }
+  { const int rc = nbest_args_ok(e, bytes, offsets, n); if (rc) return rc; }
+  if (cudaSetDevice(e->device) != cudaSuccess) { e->set_error("cudaSetDevice failed"); return SPM_ERR_CUDA; }
+  if (e->h_lat_entropy.ensure(n + 1) != cudaSuccess) { e->set_error("pinned allocation failed"); return SPM_ERR_CUDA; }
+  *entropy = e->h_lat_entropy.p;
+  if (n == 0) return SPM_OK;
+  return e->run_lattice(bytes, offsets, n, alpha, 1, 1);
+}
+
+int spm_sample_encode_and_score(spm_engine *e, const char *bytes, const uint64_t *offsets, size_t n, int num_samples,
+                                float alpha, int wor, int include_best, const int32_t **ids, const uint64_t **cand_offsets,
+                                const float **scores) {
+  if (!e || !ids || !cand_offsets || !scores) return SPM_ERR_ARG;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (e->model.model_type != SPM_UNIGRAM) {
+    e->set_error("SampleEncodeAndScore is not available for the current model.");  // sentencepiece_processor.cc:726-727
+    return SPM_ERR_UNSUPPORTED;
+  }
+  if (wor || include_best) {
+    // sampling without replacement runs Lattice::NBest with Gumbel-perturbed scores (unigram_model.cc:770-832)
+    e->set_error("SampleEncodeAndScore: wor / include_best are not on the accelerated path");
+    return SPM_ERR_UNSUPPORTED;
+  }
+  if (num_samples < 1 || num_samples > 4096) { e->set_error("num_samples must be in [1, 4096]"); return SPM_ERR_ARG; }
+  { const int rc = nbest_args_ok(e, bytes, offsets, n); if (rc) return rc; }
+  if (cudaSetDevice(e->device) != cudaSuccess) { e->set_error("cudaSetDevice failed"); return SPM_ERR_CUDA; }
+  const int rc = e->run_lattice(bytes, offsets, n, alpha, 0, num_samples);
+  if (rc) return rc;
+  if (e->lat_ids.empty()) e->lat_ids.reserve(1);
+  if (e->lat_scores.empty()) e->lat_scores.reserve(1);
+  *ids = e->lat_ids.data();
+  *cand_offsets = e->lat_offsets.data();
+  *scores = e->lat_scores.data();
+  return SPM_OK;
+}
+
 int spm_encode_spans(spm_engine *e, const char *bytes, const uint64_t *offsets, size_t n, const int32_t **ids,
                      const uint32_t **tok_end, const uint64_t **id_offsets, const char **normalized,
                      const uint64_t **norm_offsets, const uint32_t **n2o) {
-  if (!tok_end || !normalized || !norm_offsets || !n2o) return SPM_ERR_ARG;
-  return encode_host(e, bytes, offsets, n, true, ids, tok_end, id_offsets, normalized, norm_offsets, n2o);
+  if (!e || !tok_end || !normalized || !norm_offsets || !n2o) return SPM_ERR_ARG;
+  std::lock_guard<std::mutex> lk(e->mu);
+  return encode_host_locked(e, bytes, offsets, n, true, ids, tok_end, id_offsets, normalized, norm_offsets, n2o);
 }
 
 }  // extern "C"

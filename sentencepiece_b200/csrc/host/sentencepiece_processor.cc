@@ -8,6 +8,7 @@
 #include <functional>
 #include <set>
 #include <sstream>
+#include <thread>
 #include <unordered_map>
 
 #include "model_reader.h"
@@ -224,17 +225,32 @@ std::string SentencePieceProcessor::DecodeIds(const std::vector<int> &ids) const
 }
 
 namespace {
+// runs fn(lo, hi) over [0, n) on a few host threads (the container conversions around a batch call are the only
+// per-sentence host work left; the reference's Python layer uses a thread pool for the same reason,
+// python/src/sentencepiece/sentencepiece.i:235-267)
+template <typename F>
+void ParallelFor(size_t n, F fn) {
+  const size_t T = n < 16384 ? 1 : std::max<size_t>(1, std::min<size_t>(std::thread::hardware_concurrency(), 16));
+  if (T == 1) { fn(size_t{0}, n); return; }
+  std::vector<std::thread> th;
+  const size_t per = (n + T - 1) / T;
+  for (size_t t = 1; t < T; ++t) th.emplace_back(fn, std::min(n, t * per), std::min(n, (t + 1) * per));
+  fn(size_t{0}, std::min(n, per));
+  for (auto &t : th) t.join();
+}
+
 void Pack(const std::vector<std::string_view> &in, std::string *bytes, std::vector<uint64_t> *offs) {
-  size_t total = 0;
-  for (const auto &s : in) total += s.size();
-  bytes->clear();
-  bytes->reserve(total);
-  offs->assign(1, 0);
-  offs->reserve(in.size() + 1);
-  for (const auto &s : in) {
-    bytes->append(s.data(), s.size());
-    offs->push_back(bytes->size());
-  }
+  offs->resize(in.size() + 1);
+  uint64_t total = 0;
+  for (size_t i = 0; i < in.size(); ++i) { (*offs)[i] = total; total += in[i].size(); }
+  (*offs)[in.size()] = total;
+  bytes->resize(total);
+  char *dst = bytes->data();
+  const uint64_t *o = offs->data();
+  ParallelFor(in.size(), [&](size_t lo, size_t hi) {
+    for (size_t i = lo; i < hi; ++i)
+      if (!in[i].empty()) memcpy(dst + o[i], in[i].data(), in[i].size());
+  });
 }
 }  // namespace
 
@@ -251,11 +267,13 @@ util::Status SentencePieceProcessor::Encode(const std::vector<std::string_view> 
   const auto st = EncodePacked(bytes.data(), offs.data(), inputs.size(), &out, &oo);
   if (!st.ok()) return st;
   ids->resize(inputs.size());
-  for (size_t i = 0; i < inputs.size(); ++i) {
-    auto &v = (*ids)[i];
-    v.assign(out + oo[i], out + oo[i + 1]);
-    ApplyExtraIds(&v);
-  }
+  ParallelFor(inputs.size(), [&](size_t lo, size_t hi) {
+    for (size_t i = lo; i < hi; ++i) {
+      auto &v = (*ids)[i];
+      v.assign(out + oo[i], out + oo[i + 1]);
+      ApplyExtraIds(&v);
+    }
+  });
   return util::OkStatus();
 }
 
@@ -480,6 +498,78 @@ util::Status SentencePieceProcessor::SampleEncode(const std::vector<std::string_
     ApplyExtraPieces(&(*pieces)[i], &pid);
   }
   return util::OkStatus();
+}
+
+util::Status SentencePieceProcessor::CalculateEntropy(const std::vector<std::string_view> &inputs, float alpha,
+                                                      std::vector<float> *entropy) const {
+  if (!engine_) return status();
+  if (!entropy) return Internal("output container is null");
+  entropy->clear();
+  std::string bytes;
+  std::vector<uint64_t> offs;
+  Pack(inputs, &bytes, &offs);
+  const float *ent = nullptr;
+  const int rc = spm_calculate_entropy(engine_, bytes.data(), offs.data(), inputs.size(), alpha, &ent);
+  if (rc) return FromEngine(engine_, rc);
+  entropy->assign(ent, ent + inputs.size());
+  return util::OkStatus();
+}
+util::Status SentencePieceProcessor::CalculateEntropy(std::string_view input, float alpha, float *entropy) const {
+  if (!engine_) return status();
+  if (!entropy) return Internal("output container is null");
+  std::vector<float> out;
+  const auto st = CalculateEntropy(std::vector<std::string_view>{input}, alpha, &out);
+  if (!st.ok()) return st;
+  *entropy = out[0];
+  return util::OkStatus();
+}
+float SentencePieceProcessor::CalculateEntropy(std::string_view input, float alpha) const {
+  float e = 0.f;
+  CalculateEntropy(input, alpha, &e).IgnoreError();
+  return e;
+}
+
+std::vector<std::pair<std::vector<int>, float>> SentencePieceProcessor::SampleEncodeAndScoreAsIds(
+    std::string_view input, int num_samples, float alpha, bool wor, bool include_best) const {
+  std::vector<std::pair<std::vector<int>, float>> out;
+  if (!engine_) return out;
+  SeedOnce();
+  const uint64_t offs[2] = {0, input.size()};
+  const int32_t *ids;
+  const uint64_t *co;
+  const float *sc;
+  if (spm_sample_encode_and_score(engine_, input.data(), offs, 1, num_samples, alpha, wor, include_best, &ids, &co, &sc)) return out;
+  for (int c = 0; c < num_samples; ++c) {
+    out.emplace_back(std::vector<int>(ids + co[c], ids + co[c + 1]), sc[c]);
+    ApplyExtraIds(&out.back().first);
+  }
+  return out;
+}
+std::vector<std::pair<std::vector<std::string>, float>> SentencePieceProcessor::SampleEncodeAndScoreAsPieces(
+    std::string_view input, int num_samples, float alpha, bool wor, bool include_best) const {
+  std::vector<std::pair<std::vector<std::string>, float>> out;
+  if (!engine_) return out;
+  SeedOnce();
+  const uint64_t offs[2] = {0, input.size()};
+  const int32_t *sids;
+  const uint32_t *tok_end, *n2o;
+  const uint64_t *ido, *no;
+  const char *norm;
+  if (spm_encode_spans(engine_, input.data(), offs, 1, &sids, &tok_end, &ido, &norm, &no, &n2o)) return out;
+  const std::string normalized(norm + no[0], norm + no[1]);
+  const int32_t *ids;
+  const uint64_t *co;
+  const float *sc;
+  if (spm_sample_encode_and_score(engine_, input.data(), offs, 1, num_samples, alpha, wor, include_best, &ids, &co, &sc)) return out;
+  std::vector<int> pid;
+  for (int c = 0; c < num_samples; ++c) {
+    std::vector<std::string> pcs;
+    if (!PiecesFromIds(normalized, ids + co[c], co[c + 1] - co[c], &pcs)) return {};
+    pid.assign(ids + co[c], ids + co[c + 1]);
+    ApplyExtraPieces(&pcs, &pid);
+    out.emplace_back(std::move(pcs), sc[c]);
+  }
+  return out;
 }
 
 util::Status SentencePieceProcessor::NBestEncode(std::string_view input, int nbest_size,

@@ -82,6 +82,17 @@ class SentencePieceProcessor {
   std::vector<std::vector<int>> NBestEncodeAsIds(std::string_view input, int nbest_size) const;
   std::vector<std::string> SampleEncodeAsPieces(std::string_view input, int nbest_size, float alpha) const;
   std::vector<int> SampleEncodeAsIds(std::string_view input, int nbest_size, float alpha) const;
+  // ---- full-lattice operations of unigram models (sentencepiece_processor.h:364-379,401-410,483-500,521-526):
+  //      num_samples lattice samples with their scores (wor / include_best are not on the accelerated path), and the
+  //      entropy of the segmentation lattice ----
+  std::vector<std::pair<std::vector<int>, float>> SampleEncodeAndScoreAsIds(std::string_view input, int num_samples,
+                                                                            float alpha, bool wor, bool include_best) const;
+  std::vector<std::pair<std::vector<std::string>, float>> SampleEncodeAndScoreAsPieces(std::string_view input, int num_samples,
+                                                                                       float alpha, bool wor,
+                                                                                       bool include_best) const;
+  util::Status CalculateEntropy(std::string_view input, float alpha, float *entropy) const;
+  float CalculateEntropy(std::string_view input, float alpha) const;
+  util::Status CalculateEntropy(const std::vector<std::string_view> &inputs, float alpha, std::vector<float> *entropy) const;
 
   // ---- batch (what the reference's Python layer does with a thread pool,
   //      python/src/sentencepiece/sentencepiece.i:245-267) ----

@@ -140,6 +140,30 @@ class Engine:
         a = np.ctypeslib.as_array(ctypes.cast(ids, ctypes.POINTER(ctypes.c_int32)), (max(tot, 1),))[:tot].copy()
         return a, o
 
+    def calculate_entropy(self, buf, offs, alpha):
+        """CalculateEntropy per sentence of a packed batch -> float32[n]"""
+        n = len(offs) - 1
+        buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        offs = np.ascontiguousarray(offs, dtype=np.uint64)
+        ent = ctypes.c_void_p()
+        self._check(self._lib.spm_calculate_entropy(self._h, buf.ctypes.data, offs.ctypes.data, n, alpha, ctypes.byref(ent)))
+        return np.ctypeslib.as_array(ctypes.cast(ent, ctypes.POINTER(ctypes.c_float)), (max(n, 1),))[:n].copy()
+
+    def sample_encode_and_score(self, buf, offs, num_samples, alpha, wor=False, include_best=False):
+        """-> (ids, cand_offsets uint64[n*num_samples+1], scores float32[n*num_samples])"""
+        n = len(offs) - 1
+        buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        offs = np.ascontiguousarray(offs, dtype=np.uint64)
+        p = [ctypes.c_void_p() for _ in range(3)]
+        self._check(self._lib.spm_sample_encode_and_score(self._h, buf.ctypes.data, offs.ctypes.data, n, num_samples, alpha,
+                                                          int(wor), int(include_best), *[ctypes.byref(x) for x in p]))
+        nc = n * num_samples
+        co = np.ctypeslib.as_array(ctypes.cast(p[1], ctypes.POINTER(ctypes.c_uint64)), (nc + 1,)).copy()
+        tot = int(co[nc])
+        ids = np.ctypeslib.as_array(ctypes.cast(p[0], ctypes.POINTER(ctypes.c_int32)), (max(tot, 1),))[:tot].copy()
+        sc = np.ctypeslib.as_array(ctypes.cast(p[2], ctypes.POINTER(ctypes.c_float)), (max(nc, 1),))[:nc].copy()
+        return ids, co, sc
+
     def encode_device(self, d_bytes_ptr, d_offs_ptr, n, total_bytes, d_ids_ptr, ids_cap, d_id_offs_ptr, stream=None):
         """Device-resident batch (pointers are CUDA device pointers, e.g. torch data_ptr())."""
         tot = ctypes.c_uint64()

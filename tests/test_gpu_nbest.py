@@ -89,6 +89,17 @@ def test_nbest_error_behaviour(corpus_gen):
     uni = _engine("uni32k")
     with pytest.raises(RuntimeError, match="nbest_size <= 512"):
         uni.sample_encode(buf, offs, 513, 0.5)
-    with pytest.raises(RuntimeError, match="not on the accelerated path"):
-        uni.sample_encode(buf, offs, -1, 0.5)
+    with pytest.raises(RuntimeError, match="wor / include_best"):
+        uni.sample_encode_and_score(buf, offs, 3, 0.5, wor=True)
     uni.close()
+    # BPE: SampleEncode is BPE-dropout whatever nbest_size is (sentencepiece_processor.cc:689-693); only alpha <= 0
+    # equals Encode, alpha > 0 is refused rather than silently returning the deterministic encode
+    bpe = _engine("bpe32k")
+    with pytest.raises(RuntimeError, match="BPE-dropout"):
+        bpe.sample_encode(buf, offs, 1, 0.1)
+    a, ao = bpe.sample_encode(buf, offs, 64, 0.0)
+    b, bo = bpe.encode_packed(buf, offs)
+    assert np.array_equal(a, b) and np.array_equal(ao, bo)
+    with pytest.raises(RuntimeError, match="CalculateEntropy is not available"):
+        bpe.calculate_entropy(buf, offs, 0.5)
+    bpe.close()
