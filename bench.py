@@ -7,8 +7,9 @@ synthetic sentences.  The headline workload (N=1) is BASELINE.json configs[1]: 3
 
   value : whole-job sentences/s with inputs already resident in HBM (device-pointer C ABI), timed with CUDA
           events over exactly K steps, max over ranks.  With N > 1 the NCCL gather of the packed id buffers
-          (ids + per-sentence counts) to rank 0 -- the path's only exchange -- is INSIDE the timed region: every
-          rank encodes its shard in `--chunks` pieces and the gather of piece c overlaps the encode of piece c+1.
+          (ids + per-sentence counts) to rank 0 -- the path's only exchange -- is INSIDE the timed region: output
+          buffers are double-buffered, the gather of step k overlaps the encode of step k+1, and the last gathers are
+          waited for before the closing event.
   e2e   : the same metric through the host-buffer C ABI (spm_encode_ids): pinned host input, H2D + kernels +
           D2H of ids/offsets inside the timed region; `e2e_variants` adds pageable input and the C++ class
           (Encode(vector<string_view>, vector<vector<int>>*)).
@@ -352,30 +353,43 @@ def run_encode_workload(args, workload, rank, world, local_rank, scaling, light=
     d_offs = torch.from_numpy(o.astype(np.int64)).to(dev)
     stream = torch.cuda.current_stream().cuda_stream
 
-    # pieces of the shard: the gather of piece c runs (NCCL stream) while piece c+1 is encoded
+    # Output buffers are double-buffered per step: the NCCL gather of step k's ids (async, NCCL stream) overlaps the
+    # encode of step k+1; every gather is waited for before the timed region ends.  `--chunks C` (C > 1) additionally
+    # cuts a shard into C pieces per step (more, smaller launches).
     C = max(1, args.chunks) if world > 1 else 1
     cuts = [(n * c) // C for c in range(C + 1)]
     max_piece = [max((sizes[r] * (c + 1)) // C - (sizes[r] * c) // C for r in range(world)) for c in range(C)]
-    pieces = []
-    for c in range(C):
-        lo_c, hi_c = cuts[c], cuts[c + 1]
-        nb = int(o[hi_c] - o[lo_c])
-        cap_ids = nb + 4 * (hi_c - lo_c) + 1024
-        pieces.append({"lo": lo_c, "n": hi_c - lo_c, "bytes": nb, "cap": cap_ids,
-                       "ids": torch.empty(cap_ids, dtype=torch.int32, device=dev),
-                       "ido": torch.zeros(max_piece[c] + 1, dtype=torch.int64, device=dev),
-                       "recv_ids": None, "recv_ido": None})
+
+    def make_pieces():
+        out = []
+        for c in range(C):
+            lo_c, hi_c = cuts[c], cuts[c + 1]
+            nb = int(o[hi_c] - o[lo_c])
+            cap_ids = nb + 4 * (hi_c - lo_c) + 1024
+            out.append({"lo": lo_c, "n": hi_c - lo_c, "bytes": nb, "cap": cap_ids,
+                        "ids": torch.empty(cap_ids, dtype=torch.int32, device=dev),
+                        "ido": torch.zeros(max_piece[c] + 1, dtype=torch.int64, device=dev),
+                        "recv_ids": None, "recv_ido": None})
+        return out
+    slots = [make_pieces(), make_pieces()] if world > 1 else [make_pieces()]
+    inflight = [[], []]   # NCCL work handles of the gathers reading slot 0 / 1
 
     def encode_piece(p):
         return eng.encode_device(d_bytes.data_ptr(), d_offs.data_ptr() + 8 * p["lo"], p["n"], p["bytes"],
                                  p["ids"].data_ptr(), p["cap"], p["ido"].data_ptr(), stream)
 
     gathered = {"bytes": 0}
+    step_no = [0]
 
     def step():
         """one pass over the shard; returns (ids, launches, main kernel ms, all kernels ms)"""
-        works, tot, launches, main, allk, moved = [], 0, 0, 0.0, 0.0, 0
-        for p in pieces:
+        k = step_no[0] % len(slots)
+        step_no[0] += 1
+        for w in inflight[k]:   # the gather that read this slot two steps ago
+            w.wait()
+        inflight[k] = []
+        tot, launches, main, allk, moved = 0, 0, 0.0, 0.0, 0
+        for p in slots[k]:
             t = encode_piece(p)
             info = eng.info()
             tot += t
@@ -392,13 +406,17 @@ def run_encode_workload(args, workload, rank, world, local_rank, scaling, light=
                     p["recv_ids"] = [torch.empty(int(mx * 1.02) + 64, dtype=torch.int32, device=dev) for _ in range(world)]
                     p["recv_ido"] = [torch.empty_like(p["ido"]) for _ in range(world)]
                 recv = [x[:mx] for x in p["recv_ids"]] if rank == 0 else None
-                works.append(dist.gather(p["ids"][:mx], recv, dst=0, async_op=True))
-                works.append(dist.gather(p["ido"], p["recv_ido"] if rank == 0 else None, dst=0, async_op=True))
+                inflight[k].append(dist.gather(p["ids"][:mx], recv, dst=0, async_op=True))
+                inflight[k].append(dist.gather(p["ido"], p["recv_ido"] if rank == 0 else None, dst=0, async_op=True))
                 moved += 4 * int(sum(cl[1:])) + 8 * p["ido"].numel() * (world - 1)
         gathered["bytes"] = moved
-        for w in works:
-            w.wait()
         return tot, launches, main, allk
+
+    def finish_gathers():
+        for k in range(len(inflight)):
+            for w in inflight[k]:
+                w.wait()
+            inflight[k] = []
 
     def sync_all():
         if world > 1:
@@ -408,6 +426,7 @@ def run_encode_workload(args, workload, rank, world, local_rank, scaling, light=
     total_ids = 0
     for _ in range(args.warmup):
         total_ids = step()[0]
+    finish_gathers()
 
     # ---- timed: exactly K steps, CUDA events, barrier + synchronize on both sides ----
     sampler = ClockSampler(local_rank)
@@ -421,6 +440,7 @@ def run_encode_workload(args, workload, rank, world, local_rank, scaling, light=
         launches += ln
         main_ms.append(mm)
         all_ms.append(am)
+    finish_gathers()   # every step's gather completes inside the timed region
     ev1.record()
     sync_all()
     clocks = sampler.stop()
@@ -540,12 +560,13 @@ def run_encode_workload(args, workload, rank, world, local_rank, scaling, light=
             result["gather"] = {
                 "inside_timed_region": not args.no_gather, "chunks": C, "bytes_to_rank0_per_step": gathered["bytes"],
                 "encode_only_ms_per_step": enc_ms,
-                "how": "per piece: all_gather of the id counts, then async torch.distributed.gather (NCCL over NVLink) of the "
-                       "padded int32 ids and the per-sentence offsets to rank 0, overlapped with the encode of the next piece"}
+                "how": "per step: all_gather of the id counts, then async torch.distributed.gather (NCCL over NVLink) of the "
+                       "padded int32 ids and the per-sentence offsets to rank 0 from one of two output slots; the gather of step "
+                       "k overlaps the encode of step k+1 and all gathers are waited for before the closing event"}
     lib.spm_host_free(pin_bytes)
     lib.spm_host_free(pin_offs)
     eng.close()
-    del d_bytes, d_offs, pieces
+    del d_bytes, d_offs, slots
     torch.cuda.empty_cache()
     return result
 
@@ -751,7 +772,7 @@ def main():
     ap.add_argument("--workload", default="all", choices=sorted(WORKLOADS) + ["all"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--sentences", type=int, default=1_000_000, help="sentences per GPU per step (strong scaling: of the whole job)")
-    ap.add_argument("--chunks", type=int, default=4, help="N > 1: pieces per shard (gather of one overlaps the encode of the next)")
+    ap.add_argument("--chunks", type=int, default=1, help="N > 1: launches per shard and step")
     ap.add_argument("--lanes", type=int, default=0)
     ap.add_argument("--cap", type=int, default=0)
     ap.add_argument("--threads", type=int, default=0)

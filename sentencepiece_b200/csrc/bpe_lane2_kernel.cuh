@@ -320,13 +320,13 @@ __global__ void __launch_bounds__(768, 1) encode_bpe_lane2_kernel(const KModel M
                 for (uint32_t i = 0; i < plen; ++i) {
                   const uint32_t kk = off + i;
                   const uint32_t ch = (c.text_w[static_cast<size_t>(kk >> 2) * 32] >> ((kk & 3u) * 8u)) & 0xFFu;
-                  B.tmp_ids[pos + (w++)] = __ldg(M.byte_to_id + ch);
+                  __stcs(B.tmp_ids + pos + (w++), __ldg(M.byte_to_id + ch));
                 }
               } else if (!prev_unk) {
-                B.tmp_ids[pos + (w++)] = M.unk_id;
+                __stcs(B.tmp_ids + pos + (w++), M.unk_id);
               }
             } else {
-              B.tmp_ids[pos + (w++)] = static_cast<int32_t>(e & 0xFFFFFFu);
+              __stcs(B.tmp_ids + pos + (w++), static_cast<int32_t>(e & 0xFFFFFFu));
             }
             prev_unk = isunk;
             off += plen;

@@ -179,6 +179,8 @@ struct spm_engine {
   DevBuf<uint32_t> d_order, d_order_hist;  // K0: length-bucketed processing order
   int build_order(const uint64_t *d_offs, size_t n, cudaStream_t st, const uint32_t **order, uint32_t seg);
   bool sort_by_length = true;
+  DevBuf<unsigned long long> d_kstats;  // SPM_B200_KSTATS: in-kernel counters of the unigram lane kernel -> stderr
+  bool kstats = false;
   // streamed host batches (encode_host_streamed): set around run_device calls
   const uint32_t *cur_ready = nullptr;
   unsigned long long cur_off_lo = 0, cur_off_hi = ~0ull;  // valid offset range of the batch run_device is given
@@ -841,6 +843,11 @@ int spm_engine::run_device(const uint8_t *d_bytes_base, const uint64_t *d_offs, 
     B.tile_bytes = geom.tile_bytes;
 
     CUDA_TRY(cudaEventRecord(ev[0], st));
+    if (kstats) {
+      CUDA_TRY(d_kstats.ensure(16));
+      CUDA_TRY(cudaMemsetAsync(d_kstats.p, 0, 16 * sizeof(unsigned long long), st));
+      B.kstats = d_kstats.p;
+    }
     if (lane_path || bpe_lane_path) {
       uint32_t seg = cur_ready ? (1u << cur_piece_shift) : 0u;
       if (const char *v = getenv("SPM_B200_SORT_SEG")) seg = static_cast<uint32_t>(atoi(v));  // experiment knob
@@ -879,6 +886,14 @@ int spm_engine::run_device(const uint8_t *d_bytes_base, const uint64_t *d_offs, 
     CUDA_TRY(cudaMemcpyAsync(h_ctrl32.p, d_ctrl32.p, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(h_ctrl64.p, d_ctrl64.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    if (kstats) {
+      unsigned long long ks[16];
+      CUDA_TRY(cudaMemcpy(ks, d_kstats.p, sizeof ks, cudaMemcpyDeviceToHost));
+      if (ks[12])
+        fprintf(stderr, "[kstats] groups %llu: warp trips/group %.1f, lane trips/sentence %.1f (lane utilisation of K2 %.3f), starts/sentence "
+                "%.1f (whole words %.1f), normalized bytes/sentence %.1f\n", ks[12], double(ks[8]) / ks[12], double(ks[9]) / n,
+                double(ks[9]) / (32.0 * ks[8]), double(ks[10]) / n, double(ks[11]) / n, double(ks[13]) / n);
+    }
     uint32_t n_def = h_ctrl32.p[0];
     const uint32_t *def_list = d_deferred.p;
     if (n_def && (lane_path || bpe_lane_path)) {
@@ -1806,6 +1821,7 @@ static int create_common(spm_engine *e, int device, spm_engine **out) {
   if (const char *v = getenv("SPM_B200_SORT")) e->sort_by_length = atoi(v) != 0;  // A/B knob for profiles/
   if (const char *v = getenv("SPM_B200_FUSED")) e->fused_host_path = atoi(v) != 0;
   if (const char *v = getenv("SPM_B200_FASTWORDS")) e->fast_words = atoi(v) != 0;
+  if (const char *v = getenv("SPM_B200_KSTATS")) e->kstats = atoi(v) != 0;
   if (const char *v = getenv("SPM_B200_BPE_LANE_V")) e->bpe_lane_version = atoi(v);
   e->smem_optin = prop.sharedMemPerBlockOptin;
   if (cudaSetDevice(device) != cudaSuccess) return fail(SPM_ERR_CUDA, "cudaSetDevice failed");
@@ -1865,7 +1881,7 @@ void spm_engine_destroy(spm_engine *e) {
   if (e->stream) cudaStreamSynchronize(e->stream);
   e->d_link.release(); e->d_val.release(); e->d_user_link.release(); e->d_cm_units.release(); e->d_cm_lead.release();
   e->d_cm_pair.release(); e->d_id.release(); e->d_cm_solo.release(); e->d_byte_to_id.release(); e->d_cm_targets.release();
-  e->d_types.release(); e->d_scores.release(); e->d_word_safe.release(); e->d_word_fast.release(); e->d_bytes.release(); e->d_tmp_norm.release(); e->d_norm.release();
+  e->d_types.release(); e->d_scores.release(); e->d_word_safe.release(); e->d_word_fast.release(); e->d_kstats.release(); e->d_bytes.release(); e->d_tmp_norm.release(); e->d_norm.release();
   e->d_long_scratch.release(); e->d_offsets.release(); e->d_tmp_ids.release(); e->d_ids.release();
   e->d_tmp_tok_end.release(); e->d_tok_end.release(); e->d_tmp_n2o.release(); e->d_n2o.release();
   e->d_sent_count.release(); e->d_norm_len.release(); e->d_deferred.release(); e->d_deferred2.release(); e->d_long_list.release();

@@ -874,9 +874,9 @@ __global__ void __launch_bounds__(256) scan_write_gather_kernel(const uint32_t *
     const unsigned long long d0 = sh_off[k];
     if (d0 + cnt > dst_cap) continue;
     const unsigned long long s0 = src_start[i];
-    for (uint32_t t = lane8; t < cnt; t += 8) {
-      dst[d0 + t] = src[s0 + t];
-      if (dst2) dst2[d0 + t] = src2[s0 + t];
+    for (uint32_t t = lane8; t < cnt; t += 8) {  // streaming both ways
+      __stcs(dst + d0 + t, __ldcs(src + s0 + t));
+      if (dst2) __stcs(dst2 + d0 + t, __ldcs(src2 + s0 + t));
     }
   }
 }

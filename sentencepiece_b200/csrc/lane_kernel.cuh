@@ -127,7 +127,7 @@ struct ByteStream {
     if (++wi == 4) {
       wi = 0;
       cur = nxt;
-      nxt = cp < cend ? __ldg(cp) : make_uint4(0, 0, 0, 0);
+      nxt = cp < cend ? __ldcs(cp) : make_uint4(0, 0, 0, 0);
       ++cp;
     }
     return w;
@@ -136,8 +136,8 @@ struct ByteStream {
     const uintptr_t a = reinterpret_cast<uintptr_t>(p);
     const uint4 *c0 = reinterpret_cast<const uint4 *>(a & ~static_cast<uintptr_t>(15));
     cend = reinterpret_cast<const uint4 *>((reinterpret_cast<uintptr_t>(hi) + 15) & ~static_cast<uintptr_t>(15));
-    cur = __ldg(c0);
-    nxt = c0 + 1 < cend ? __ldg(c0 + 1) : make_uint4(0, 0, 0, 0);
+    cur = __ldcs(c0);  // streaming (evict-first) loads: the input is read once and must not push the slabs out of L2
+    nxt = c0 + 1 < cend ? __ldcs(c0 + 1) : make_uint4(0, 0, 0, 0);
     cp = c0 + 2;
     wi = static_cast<uint32_t>((a & 15) >> 2);
     const uint32_t mis = static_cast<uint32_t>(a & 3);
@@ -446,13 +446,13 @@ __device__ __forceinline__ void lane_finish(const KModel &M, const KBatch &B, co
               for (uint32_t i = 0; i < plen; ++i) {
                 const uint32_t kk = want - 1 - i;
                 const uint32_t ch = (c.text_w[static_cast<size_t>(kk >> 2) * 32] >> ((kk & 3u) * 8u)) & 0xFFu;
-                B.tmp_ids[pos + (--w)] = __ldg(M.byte_to_id + ch);
+                __stcs(B.tmp_ids + pos + (--w), __ldg(M.byte_to_id + ch));
               }
             } else if (!prev_unk) {
-              B.tmp_ids[pos + (--w)] = M.unk_id;
+              __stcs(B.tmp_ids + pos + (--w), M.unk_id);
             }
           } else {
-            B.tmp_ids[pos + (--w)] = __ldg(M.trie_id + idx);
+            __stcs(B.tmp_ids + pos + (--w), __ldg(M.trie_id + idx));  // streaming store
           }
           prev_unk = isunk;
           want -= plen;
@@ -567,7 +567,12 @@ __global__ void __launch_bounds__(1024, 1) encode_unigram_lane_kernel(const KMod
       if (mblen > n) mblen = n;
       cur = window_low();
     }
+    // optional counters (engine: SPM_B200_KSTATS; device-resident path only): [8] warp trips, [9] lane trips,
+    // [10] starts retired, [11] whole words, [12] groups, [13] normalized bytes
+    const bool kst = B.kstats != nullptr && B.seg_done == nullptr;
+    uint32_t st_trips = 0, st_lane = 0, st_starts = 0, st_fast = 0;
     while (__any_sync(0xFFFFFFFFu, !done)) {
+      if (kst) { ++st_trips; st_lane += !done; }
       if (!done) {
         bool end_walk = true;
         if (k < n) {
@@ -656,6 +661,7 @@ __global__ void __launch_bounds__(1024, 1) encode_unigram_lane_kernel(const KMod
           }
           const uint32_t s_old = s;
           uint32_t steplog;
+          if (kst) { ++st_starts; st_fast += fast; }
           if (fast) {
             // the piece was relaxed into k when the walk stepped onto its node; nothing else can win there
             ss += (k - s) * 32u;
@@ -703,6 +709,20 @@ __global__ void __launch_bounds__(1024, 1) encode_unigram_lane_kernel(const KMod
             has_single = false;
           }
         }
+      }
+    }
+    if (kst) {
+      typedef unsigned long long ull;
+      uint32_t nb = n;
+      for (int d = 16; d > 0; d >>= 1) {
+        st_lane += __shfl_xor_sync(0xFFFFFFFFu, st_lane, d);
+        st_starts += __shfl_xor_sync(0xFFFFFFFFu, st_starts, d);
+        st_fast += __shfl_xor_sync(0xFFFFFFFFu, st_fast, d);
+        nb += __shfl_xor_sync(0xFFFFFFFFu, nb, d);
+      }
+      if (lane == 0) {
+        atomicAdd(B.kstats + 8, ull(st_trips)); atomicAdd(B.kstats + 9, ull(st_lane)); atomicAdd(B.kstats + 10, ull(st_starts));
+        atomicAdd(B.kstats + 11, ull(st_fast)); atomicAdd(B.kstats + 12, ull(1)); atomicAdd(B.kstats + 13, ull(nb));
       }
     }
     lane_finish(M, B, c, n, nlog, lane, have, defer, sent, bf);  // K4

@@ -1,9 +1,9 @@
 """A/B of the lane-kernel generations on a B200: ids must be identical, times are printed.
 
-usage: python tools/lane_ab.py [model:kind ...] [--n N] [--variants "V=1;V=2,FW=0;V=2,FW=1,Q=12,W=8,R=8,T=768"]
+usage: python tools/lane_ab.py [model:kind ...] [--n N] [--variants "FW=0;FW=1;BV=1;BV=2,T=704"]
 Each variant is a ';'-separated item of ','-separated KEY=VALUE knobs:
-  V lane kernel version (SPM_B200_LANE_V), FW whole-word shortcut, Q queue entries, W/R walk/relax thresholds,
-  T threads per CTA, BV BPE lane kernel version.
+  FW whole-word shortcut (SPM_B200_FASTWORDS), S length ordering (SPM_B200_SORT),
+  T threads per CTA, BV BPE lane kernel version (SPM_B200_BPE_LANE_V).
 """
 import argparse
 import os
@@ -18,14 +18,14 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 import corpus  # noqa: E402
 from sentencepiece_b200 import Engine  # noqa: E402
 
-ENV = {"V": "SPM_B200_LANE_V", "FW": "SPM_B200_FASTWORDS", "Q": "SPM_B200_LANE_Q", "W": "SPM_B200_LANE_WMIN",
-       "R": "SPM_B200_LANE_RMIN", "BV": "SPM_B200_BPE_LANE_V", "S": "SPM_B200_SORT"}
+ENV = {"FW": "SPM_B200_FASTWORDS",
+       "BV": "SPM_B200_BPE_LANE_V", "S": "SPM_B200_SORT"}
 
 ap = argparse.ArgumentParser()
 ap.add_argument("workloads", nargs="*", default=["uni32k:en"])
 ap.add_argument("--n", type=int, default=1_000_000)
 ap.add_argument("--reps", type=int, default=4)
-ap.add_argument("--variants", default="V=1;V=2,FW=0;V=2,FW=1")
+ap.add_argument("--variants", default="FW=0;FW=1")
 args = ap.parse_args()
 
 g = corpus.CorpusGen()
