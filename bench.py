@@ -586,13 +586,21 @@ def run_decode_workload(args, rank, world, local_rank):
     n = args.sentences
     g = corpus.CorpusGen()
     buf, offs = g.fill("en", CORPUS_SEED, n, first=rank * n)
-    ids, ido = eng.encode_packed(buf, offs)          # host copies of the ids: the decode input
-    total_ids = int(ido[-1])
+    ids0, ido0 = eng.encode_packed(buf, offs)          # the ids to decode ...
+    total_ids = int(ido0[-1])
     lib = eng._lib
+    # ... in pinned host memory (like the encode workloads' inputs); the pageable variant is measured separately
+    p_ids = lib.spm_host_alloc(4 * total_ids + 64)
+    p_ido = lib.spm_host_alloc(8 * (n + 1))
+    ids = np.ctypeslib.as_array(ctypes.cast(p_ids, ctypes.POINTER(ctypes.c_int32)), (max(total_ids, 1),))[:total_ids]
+    ido = np.ctypeslib.as_array(ctypes.cast(p_ido, ctypes.POINTER(ctypes.c_uint64)), (n + 1,))
+    ids[:] = ids0
+    ido[:] = ido0
     text_p, to_p = ctypes.c_void_p(), ctypes.c_void_p()
 
-    def step():
-        rc = lib.spm_decode_ids(eng._h, ids.ctypes.data, ido.ctypes.data, n, ctypes.byref(text_p), ctypes.byref(to_p))
+    def step(src=None):
+        a = ids if src is None else src
+        rc = lib.spm_decode_ids(eng._h, a.ctypes.data, ido.ctypes.data, n, ctypes.byref(text_p), ctypes.byref(to_p))
         if rc:
             raise RuntimeError(lib.spm_last_error(eng._h).decode())
     for _ in range(max(3, args.warmup)):
@@ -622,6 +630,21 @@ def run_decode_workload(args, rank, world, local_rank):
         t = torch.tensor([dt, kernel_ms, main_ms], device=torch.device("cuda", local_rank))
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt, kernel_ms, main_ms = (float(x) for x in t.tolist())
+    variants = None
+    if rank == 0 and not args.no_variants:
+        best = None
+        for _ in range(3):
+            t1 = time.perf_counter()
+            step(ids0)
+            d1 = time.perf_counter() - t1
+            best = d1 if best is None else min(best, d1)
+        variants = {"pageable_input_spm_decode_ids": {"value": n / best, "unit": "sentences/s", "ms_per_step": best * 1e3,
+                                                      "note": "ids in ordinary (pageable) host memory: the engine stages them "
+                                                              "through pinned buffers; bounded by the host's memcpy bandwidth"}}
+    ids = ids0
+    ido = ido0
+    lib.spm_host_free(p_ids)
+    lib.spm_host_free(p_ido)
     eng.close()
     if rank != 0:
         return None
@@ -652,10 +675,11 @@ def run_decode_workload(args, rank, world, local_rank):
                 "e2e_is": "wall clock of spm_decode_ids incl. H2D of the ids and D2H of the text"},
         "clocks": clocks,
         "e2e": {"value": world * n * args.steps / dt, "unit": "sentences/s", "ms_per_step": dt / args.steps * 1e3,
-                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "gpu_launches": int(launches),
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "api": "spm_decode_ids (host buffers, pinned input)"},
+        "e2e_variants": variants, "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                     "traffic": None, "kernel": "decode_warp_kernel", "kernel_ms": main_ms / args.steps,
+                     "traffic": (load_traffic("decode_unigram32k_en", n) or {}).get("traffic_bytes"), "kernel": "decode_warp_kernel",
+                     "kernel_ms": main_ms / args.steps,
                      "algorithmic_bytes_per_step": alg, "peak_source": peak_src},
         "cpu_baseline": cpu, "parity": parity}
 
@@ -745,7 +769,8 @@ def run_sample_workload(args, rank, world, local_rank):
             "e2e": {"value": world * n * steps / dt, "unit": "sentences/s", "ms_per_step": dt / steps * 1e3,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "traffic": (load_traffic("sample_nbest64_en", n) or {}).get("traffic_bytes"),
                          "kernel": "nbest_lane_kernel", "kernel_ms": main_ms / steps, "algorithmic_bytes_per_step": alg,
                          "peak_source": peak_src,
                          "note": "input + the 64-best lists (ids and scores) + sampled ids; the A* agenda / hypothesis pool "

@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(768, 1) encode_bpe_lane_kernel(const KModel M,
         }
       }
     }
-    lane_drain(B, first, lane);  // K6 (fused host path only)
+    lane_drain(B, sent, have, lane);  // K6 (fused host path only)
     __syncwarp();
   }
 }

@@ -34,7 +34,10 @@ struct KModel {
   const uint32_t *trie_link;
   const uint32_t *trie_val;
   const int32_t *trie_id;
-  const uint2 *trie_node2;  // {link, child mask} interleaved (lane kernel: one 8-byte load per transition)
+  const uint2 *trie_node2;  // {link, child mask} interleaved (one 8-byte load per transition)
+  // {link, child mask, score bits, word_safe} (unigram lane kernel: one 16-byte load per transition brings the piece
+  // score and the whole-word limit along, so neither costs a second dependent lookup)
+  const uint4 *trie_node4;
   uint32_t trie_units;
   uint32_t hot_link;   // units of trie_link staged into shared memory by each CTA (multiple of 4)
   uint32_t hot_val;    // units of trie_val staged (multiple of 4)

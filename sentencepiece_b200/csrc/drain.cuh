@@ -4,13 +4,15 @@
 // batch.  The ids of a sentence land in a temporary buffer in completion order (K4); the result
 // the reference-facing API returns is ids in INPUT order plus id_offsets[n + 1]
 // (SentencePieceProcessor::Encode over a list, sentencepiece_processor.cc:392-403).  The batch is
-// cut into segments of 2^seg_shift consecutive sentences, each segment is length-ordered among
-// itself (order_kernel.cuh), and the warp that finishes the LAST sentence group of a segment
-// compacts that segment:
+// cut into segments of 2^seg_shift consecutive sentences; the processing order is sorted over whole
+// input pieces (2^piece_shift sentences, order_kernel.cuh), so a group of 32 lanes may hold
+// sentences of many segments: finished sentences are counted per segment, and the warp that brings
+// a segment's count to its size compacts that segment:
 //   1. exclusive scan of the segment's id counts, segment total published;
 //   2. decoupled look-back over the earlier segments' {total, inclusive prefix} words gives the
-//      segment's first output position (all warps are resident, and the work counter hands out
-//      groups in segment order, so every earlier segment is held by a running warp);
+//      segment's first output position.  An earlier segment that is not finished yet is waited for:
+//      one warp per finished-but-blocked segment (at most the segments of a piece or two) spins
+//      while the other resident warps keep taking groups, so the wait always ends;
 //   3. id_offsets (to pinned host memory) and the ids (to the device result buffer) are written;
 //   4. the run of finished segments is extended and its id count stored to a pinned host word: the
 //      host polls it and fetches the finished prefix with the copy engine while later segments are
@@ -33,21 +35,43 @@ __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
   return v;
 }
 
-// Called by every warp after it has stored a group's results (sent_start / sent_count / tmp_ids).
-// `first` is the group's position in processing order.
-__device__ __forceinline__ void lane_drain(const KBatch &B, uint32_t first, uint32_t lane) {
+// Compaction of a finished segment (warp-collective), in two steps: drain_publish scans the segment's counts and
+// publishes its total; drain_finish finds the segment's output position (look-back over the earlier segments, which
+// may have to be waited for) and copies.  A warp that finishes several segments at once publishes ALL their totals
+// before it waits for anything: a wait only ever depends on totals, and those are out before any waiting starts.
+__device__ __forceinline__ void drain_publish(const KBatch &B, uint32_t seg, uint32_t lane);
+__device__ __forceinline__ void drain_finish(const KBatch &B, uint32_t seg, uint32_t lane);
+
+// Called by every warp after it has stored a group's results (sent_start / sent_count / tmp_ids): `sent` is the lane's
+// sentence (valid when `have`).  The processing order may mix the sentences of many segments in one group (the order
+// is sorted over a whole input piece, drain segments are much smaller), so completion is counted per SENTENCE: the
+// lanes of a group that share a segment add their count with one atomic, and the warp that brings a segment's count
+// to its size compacts it.
+__device__ __forceinline__ void lane_drain(const KBatch &B, uint32_t sent, bool have, uint32_t lane) {
   if (!B.seg_done) return;
-  const uint32_t seg = first >> B.seg_shift;
+  __threadfence();  // release: this group's results before the counters
+  const uint32_t seg = have ? sent >> B.seg_shift : 0xFFFFFFFFu;
+  const uint32_t peers = __match_any_sync(0xFFFFFFFFu, seg);
+  const uint32_t leader = static_cast<uint32_t>(__ffs(peers)) - 1u;
+  bool completes = false;
+  if (have && lane == leader) {
+    const uint32_t cnt = static_cast<uint32_t>(__popc(peers));
+    const uint32_t seg_lo = seg << B.seg_shift;
+    const uint32_t seg_n = min(B.n - seg_lo, 1u << B.seg_shift);
+    completes = atomicAdd(B.seg_done + seg, cnt) + cnt == seg_n;
+  }
+  const uint32_t done = __ballot_sync(0xFFFFFFFFu, completes);
+  if (!done) return;  // the usual case
+  __threadfence();  // acquire: the other groups' results
+  for (uint32_t todo = done; todo; todo &= todo - 1u)   // one segment at a time, the whole warp works on it
+    drain_publish(B, __shfl_sync(0xFFFFFFFFu, seg, static_cast<uint32_t>(__ffs(todo)) - 1u), lane);
+  for (uint32_t todo = done; todo; todo &= todo - 1u)
+    drain_finish(B, __shfl_sync(0xFFFFFFFFu, seg, static_cast<uint32_t>(__ffs(todo)) - 1u), lane);
+}
+
+__device__ __forceinline__ void drain_publish(const KBatch &B, uint32_t seg, uint32_t lane) {
   const uint32_t seg_lo = seg << B.seg_shift;
   const uint32_t seg_n = min(B.n - seg_lo, 1u << B.seg_shift);
-  __threadfence();  // release: this group's results before the counter
-  uint32_t prev = 0;
-  if (lane == 0) prev = atomicAdd(B.seg_done + seg, 1u);
-  prev = __shfl_sync(0xFFFFFFFFu, prev, 0);
-  if (prev + 1 != (seg_n + 31) / 32) return;
-  __threadfence();  // acquire: the other groups' results
-  const long long t_start = clock64();
-  long long t_lb = 0;
   // ---- 1. scan of the counts; relative offsets parked in sent_rel ----
   uint32_t run = 0;
   for (uint32_t j = 0; j < seg_n; j += 32) {
@@ -62,11 +86,19 @@ __device__ __forceinline__ void lane_drain(const KBatch &B, uint32_t first, uint
     if (j + lane < seg_n) B.sent_rel[i] = run + incl - cnt;
     run += __shfl_sync(0xFFFFFFFFu, incl, 31);
   }
-  const unsigned long long total = run;
   if (lane == 0) {
-    *reinterpret_cast<volatile unsigned long long *>(B.seg_total + seg) = total | kSegFlag;
+    *reinterpret_cast<volatile unsigned long long *>(B.seg_total + seg) = static_cast<unsigned long long>(run) | kSegFlag;
     __threadfence();
   }
+  __syncwarp();
+}
+
+__device__ __forceinline__ void drain_finish(const KBatch &B, uint32_t seg, uint32_t lane) {
+  const uint32_t seg_lo = seg << B.seg_shift;
+  const uint32_t seg_n = min(B.n - seg_lo, 1u << B.seg_shift);
+  const long long t_start = clock64();
+  long long t_lb = 0;
+  const unsigned long long total = ld_volatile_u64(B.seg_total + seg) & ~kSegFlag;
   // ---- 2. decoupled look-back, 32 predecessors per step ----
   const long long t_lb0 = clock64();
   unsigned long long prefix = 0;
@@ -83,6 +115,11 @@ __device__ __forceinline__ void lane_drain(const KBatch &B, uint32_t first, uint
     const uint32_t need = first_p >= 32u ? 0xFFFFFFFFu : ((1u << first_p) - 1u);
     if ((has_any & need) != need) {  // a nearer segment has published nothing yet
       __nanosleep(100);
+      // bounded like the input wait: ~3 s without progress fails the call (status bit 2) instead of hanging the GPU
+      if (clock64() - t_lb0 > 6000000000ll || (*reinterpret_cast<const volatile uint32_t *>(B.status + 1) & 4u)) {
+        if (lane == 0) atomicOr(B.status + 1, 4u);
+        break;
+      }
       continue;
     }
     unsigned long long mine = 0;

@@ -143,6 +143,7 @@ struct spm_engine {
   DevBuf<uint8_t> d_cm_targets, d_types;
   DevBuf<float> d_scores;
   DevBuf<uint16_t> d_word_safe;
+  DevBuf<uint4> d_node4;
   DevBuf<uint32_t> d_word_fast;
   int bpe_lane_version = 2;  // SPM_B200_BPE_LANE_V
   bool fast_words = true;  // SPM_B200_FASTWORDS
@@ -245,6 +246,13 @@ struct spm_engine {
   PinBuf<uint64_t> h_dec_text_offsets;
   bool dec_ready = false;
   int ensure_decode_tables();
+  // large host batches: chunked three-stage pipeline (staged H2D of the ids / decode kernels / D2H of the text)
+  DevBuf<int32_t> p_dec_ids[2];
+  DevBuf<uint8_t> p_dec_text[2];
+  DevBuf<unsigned long long> p_dec_toff[2];
+  PinBuf<uint8_t> h_stage[2];
+  int decode_host_pipelined(const int32_t *ids, const uint64_t *id_offsets, size_t n, const char **text,
+                            const uint64_t **text_offsets);
   // n-best / sampling
   DevBuf<uint8_t> d_nb_scratch;
   DevBuf<unsigned long long> d_cand_start, d_cand_offsets;
@@ -634,6 +642,12 @@ int spm_engine::upload_word_safe() {
   CUDA_TRY(d_word_fast.upload(fastw));
   km.word_safe = d_word_safe.p;
   km.word_fast = d_word_fast.p;
+  {
+    std::vector<uint4> n4(trie.link.size());
+    for (size_t u = 0; u < trie.link.size(); ++u) n4[u] = make_uint4(trie.link[u], trie.cmask[u], trie.val[u], safe[u]);
+    CUDA_TRY(d_node4.upload(n4));
+    km.trie_node4 = d_node4.p;
+  }
   return SPM_OK;
 }
 
@@ -1308,7 +1322,8 @@ int spm_engine::encode_host_fused(const char *bytes, const uint64_t *offsets, si
   const auto t_begin = std::chrono::steady_clock::now();
   auto now_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
   uint32_t kPieceShift = 15;
-  constexpr uint32_t kSegShift = 10;
+  uint32_t kSegShift = 10;
+  if (const char *v = getenv("SPM_B200_SEG_SHIFT")) kSegShift = std::min<uint32_t>(kPieceShift, std::max(8, atoi(v)));  // experiment knob
   if (const char *v = getenv("SPM_B200_PIECE_SHIFT")) kPieceShift = std::min(20, std::max(10, atoi(v)));
   const size_t kPiece = size_t{1} << kPieceShift;
   const size_t P = (n + kPiece - 1) / kPiece;
@@ -1417,7 +1432,9 @@ int spm_engine::encode_host_fused(const char *bytes, const uint64_t *offsets, si
   B.out_off_base = 0;
   B.kstats = trace ? d_ctrl64.p + 4 : nullptr;
   CUDA_TRY(cudaEventRecord(ev[0], st));
-  { const int rc = build_order(s_offsets.p, n, st, &B.order, 1u << kSegShift); if (rc) return rc; }
+  // processing order: sorted over whole input pieces (the unit in which the bytes arrive); compaction works on the much
+  // smaller drain segments, whose completion is counted per sentence (drain.cuh)
+  { const int rc = build_order(s_offsets.p, n, st, &B.order, 1u << kPieceShift); if (rc) return rc; }
   if (!B.order) { set_error("fused path needs the segment order"); return SPM_ERR_ARG; }
   if (bpe && lg.version == 2) encode_bpe_lane2_kernel<<<grid, lane_threads, smem, st>>>(M, B, d_lane_slabs.p, lane_cap);
   else if (bpe) encode_bpe_lane_kernel<<<grid, lane_threads, smem, st>>>(M, B, d_lane_slabs.p, lane_cap);
@@ -1456,6 +1473,7 @@ int spm_engine::encode_host_fused(const char *bytes, const uint64_t *offsets, si
   if (bad) { cudaDeviceSynchronize(); set_error("offsets must be non-decreasing"); return SPM_ERR_ARG; }
   if (feed_rc) { cudaDeviceSynchronize(); set_error("host-to-device copy of a streamed batch failed"); return SPM_ERR_CUDA; }
   if (h_ctrl32.p[1] & 2u) { set_error("encode failed: the host-to-device copy of a streamed batch made no progress for 3 s"); return SPM_ERR_CUDA; }
+  if (h_ctrl32.p[1] & 4u) { set_error("encode failed: the in-kernel compaction waited 3 s for an earlier segment"); return SPM_ERR_ENCODE; }
   if (h_ctrl32.p[1]) { set_error("encode failed: internal consistency check (status " + std::to_string(h_ctrl32.p[1]) + ")"); return SPM_ERR_ENCODE; }
   if (h_ctrl32.p[0] || h_ctrl32.p[2]) {
     // deferred sentences or a buffer that was too small: the chunked path has the second-chance and retry logic
@@ -1530,6 +1548,198 @@ int spm_engine::ensure_decode_tables() {
   return SPM_OK;
 }
 
+// Host-to-device copy of caller memory: pinned memory goes straight to the copy engine; pageable memory is first
+// copied into a pinned staging buffer by a few host threads (the driver's own staging of pageable memory is
+// single-threaded and synchronous), then handed to the copy engine.
+namespace {
+bool is_pinned(const void *p) {
+  cudaPointerAttributes a{};
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+void parallel_memcpy(void *dst, const void *src, size_t bytes) {
+  const size_t T = bytes < (4u << 20) ? 1 : std::min<size_t>(8, std::max<size_t>(1, std::thread::hardware_concurrency() / 2));
+  if (T == 1) { memcpy(dst, src, bytes); return; }
+  std::vector<std::thread> th;
+  const size_t per = ((bytes + T - 1) / T + 63) & ~size_t{63};
+  for (size_t t = 1; t < T; ++t) {
+    const size_t lo = std::min(bytes, t * per), hi = std::min(bytes, (t + 1) * per);
+    if (hi > lo) th.emplace_back([=]() { memcpy(static_cast<char *>(dst) + lo, static_cast<const char *>(src) + lo, hi - lo); });
+  }
+  memcpy(dst, src, std::min(bytes, per));
+  for (auto &t : th) t.join();
+}
+}  // namespace
+
+// Decode of a large host batch: chunks of id lists flow through H2D (staged when the caller's memory is pageable),
+// decode + scan + gather, and D2H of the text on three streams; inputs and outputs are double buffered.
+int spm_engine::decode_host_pipelined(const int32_t *ids, const uint64_t *id_offsets, size_t n, const char **text,
+                                      const uint64_t **text_offsets) {
+  if (!s_h2d) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&s_h2d, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&s_d2h, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; ++k) {
+      CUDA_TRY(cudaEventCreateWithFlags(&ev_in[k], cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&ev_out[k], cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&ev_d2h[k], cudaEventDisableTiming));
+    }
+  }
+  cudaStream_t st = stream;
+  const bool trace = getenv("SPM_B200_TRACE") != nullptr;
+  const auto t_begin = std::chrono::steady_clock::now();
+  auto now_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
+  const size_t chunk = 131072;
+  const size_t C = (n + chunk - 1) / chunk;
+  const bool pinned_in = is_pinned(ids);
+  uint64_t max_ids = 0;
+  for (size_t c = 0; c < C; ++c) max_ids = std::max<uint64_t>(max_ids, id_offsets[std::min(n, (c + 1) * chunk)] - id_offsets[c * chunk]);
+  const uint64_t total_ids = id_offsets[n] - id_offsets[0];
+  for (int k = 0; k < 2; ++k) {
+    CUDA_TRY(p_dec_ids[k].ensure(max_ids + 1));
+    CUDA_TRY(p_offsets[k].ensure(chunk + 1));
+    CUDA_TRY(p_dec_toff[k].ensure(chunk + 1));
+    if (!pinned_in) CUDA_TRY(h_stage[k].ensure(max_ids * sizeof(int32_t) + 64));
+  }
+  CUDA_TRY(h_dec_text_offsets.ensure(n + 1));
+  CUDA_TRY(h_dec_text.ensure(std::max<size_t>(h_dec_text.cap, total_ids * 5 + 16 * n + 4096)));
+  CUDA_TRY(d_sent_start.ensure(chunk));
+  CUDA_TRY(d_sent_count.ensure(chunk));
+  CUDA_TRY(d_ctrl32.ensure(16));
+  CUDA_TRY(d_ctrl64.ensure(8));
+  CUDA_TRY(h_ctrl32.ensure(16));
+  CUDA_TRY(h_ctrl64.ensure(8));
+  const uint32_t nb_max = (static_cast<uint32_t>(chunk) + kScanChunk - 1) / kScanChunk;
+  CUDA_TRY(d_block_sums.ensure(nb_max + 1));
+  auto issue_h2d = [&](size_t c) -> int {
+    const int k = static_cast<int>(c & 1);
+    const size_t lo = c * chunk, hi = std::min(n, lo + chunk);
+    const uint64_t cnt = id_offsets[hi] - id_offsets[lo];
+    if (c >= 2) {
+      CUDA_TRY(cudaStreamWaitEvent(s_h2d, ev_out[k], 0));  // the slot's previous chunk has been decoded
+      if (!pinned_in) CUDA_TRY(cudaEventSynchronize(ev_in[k]));  // ... and its staging buffer has been read
+    }
+    const void *src = ids + id_offsets[lo];
+    if (cnt && !pinned_in) {
+      parallel_memcpy(h_stage[k].p, src, cnt * sizeof(int32_t));
+      src = h_stage[k].p;
+    }
+    if (cnt) CUDA_TRY(cudaMemcpyAsync(p_dec_ids[k].p, src, cnt * sizeof(int32_t), cudaMemcpyHostToDevice, s_h2d));
+    CUDA_TRY(cudaMemcpyAsync(p_offsets[k].p, id_offsets + lo, (hi - lo + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s_h2d));
+    CUDA_TRY(cudaEventRecord(ev_in[k], s_h2d));
+    return SPM_OK;
+  };
+  uint64_t launches = 0;
+  float main_ms = 0.f, all_ms = 0.f;  // decode kernels; scan + gather kernels
+  unsigned long long text_base = 0;
+  { const int rc = issue_h2d(0); if (rc) return rc; }
+  for (size_t c = 0; c < C; ++c) {
+    const int k = static_cast<int>(c & 1);
+    const size_t lo = c * chunk, hi = std::min(n, lo + chunk);
+    const uint32_t m = static_cast<uint32_t>(hi - lo);
+    const uint64_t cnt = id_offsets[hi] - id_offsets[lo];
+    CUDA_TRY(cudaStreamWaitEvent(st, ev_in[k], 0));
+    if (c >= 2) CUDA_TRY(cudaStreamWaitEvent(st, ev_d2h[k], 0));  // the slot's previous text has left the GPU
+    unsigned long long tmp_cap = cnt * 6 + 16ull * m + (1u << 20);
+    unsigned long long tot = 0;
+    bool staged_next = false;
+    for (int attempt = 0; attempt < 3; ++attempt) {
+      CUDA_TRY(d_dec_tmp.ensure(tmp_cap));
+      CUDA_TRY(cudaMemsetAsync(d_ctrl32.p, 0, 16 * sizeof(uint32_t), st));
+      CUDA_TRY(cudaMemsetAsync(d_ctrl64.p, 0, 8 * sizeof(unsigned long long), st));
+      KDecode D{};
+      D.ids = p_dec_ids[k].p - id_offsets[lo];
+      D.id_offsets = reinterpret_cast<const unsigned long long *>(p_offsets[k].p);
+      D.n = m;
+      D.vocab = model.vocab_size();
+      D.dec_off = d_dec_off.p;
+      D.dec_bytes = d_dec_bytes.p;
+      D.dec_info = d_dec_info.p;
+      D.strip = (model.add_dummy_prefix || model.remove_extra_whitespaces) ? 1u : 0u;
+      D.rm = model.remove_extra_whitespaces ? 1u : 0u;
+      D.tmp = d_dec_tmp.p;
+      D.tmp_cap = tmp_cap;
+      D.cursor = d_ctrl64.p;
+      D.sent_start = d_sent_start.p;
+      D.sent_count = d_sent_count.p;
+      D.status = d_ctrl32.p;
+      CUDA_TRY(cudaEventRecord(ev[0], st));
+      const int grid = static_cast<int>(std::min<size_t>(static_cast<size_t>(sm_count) * 8, (m + 7) / 8));
+      decode_warp_kernel<<<grid, 256, 0, st>>>(D);
+      CUDA_TRY(cudaGetLastError());
+      CUDA_TRY(cudaEventRecord(ev[1], st));
+      ++launches;
+      CUDA_TRY(cudaMemcpyAsync(h_ctrl32.p, d_ctrl32.p, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaMemcpyAsync(h_ctrl64.p, d_ctrl64.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+      // the next chunk's ids are staged / queued while this chunk's kernel runs
+      if (!staged_next && c + 1 < C) { const int rc = issue_h2d(c + 1); if (rc) { cudaDeviceSynchronize(); return rc; } }
+      staged_next = true;
+      CUDA_TRY(cudaStreamSynchronize(st));
+      float a = 0.f;
+      if (cudaEventElapsedTime(&a, ev[0], ev[1]) == cudaSuccess) main_ms += a;
+      if (trace) fprintf(stderr, "[trace] decode chunk %zu: kernel done at %.3f ms (kernel %.3f ms, input %s)\n", c, now_ms(), a,
+                         pinned_in ? "pinned" : "pageable, staged");
+      if (h_ctrl32.p[1] == 2u) {  // :915-918
+        cudaDeviceSynchronize();
+        set_error("Invalid id: " + std::to_string(static_cast<int32_t>(h_ctrl32.p[3])));
+        return SPM_ERR_ARG;
+      }
+      if (h_ctrl32.p[1] == 1u) {
+        cudaDeviceSynchronize();
+        set_error("Decode: byte piece of id " + std::to_string(h_ctrl32.p[3]) + " is not of the form <0xXX>");
+        return SPM_ERR_ENCODE;
+      }
+      tot = h_ctrl64.p[0];
+      if (h_ctrl32.p[2]) { tmp_cap = tot + 1024; continue; }
+      break;
+    }
+    if (h_ctrl32.p[2]) { cudaDeviceSynchronize(); set_error("Decode: temporary buffer overflow persisted"); return SPM_ERR_CAPACITY; }
+    const uint32_t nb = (m + kScanChunk - 1) / kScanChunk;
+    CUDA_TRY(p_dec_text[k].ensure(tot + 16));
+    if (c > 0) {  // the previous chunk's scan + gather finished before this chunk's kernel did
+      float g = 0.f;
+      if (cudaEventElapsedTime(&g, ev[2], ev[3]) == cudaSuccess) all_ms += g;
+    }
+    CUDA_TRY(cudaEventRecord(ev[2], st));
+    scan_block_sums_kernel<<<nb, 256, 0, st>>>(d_sent_count.p, m, d_block_sums.p, 0);
+    scan_block_prefix_kernel<<<1, 1024, 0, st>>>(d_block_sums.p, nb, d_ctrl64.p + 2);
+    scan_write_gather_kernel<uint8_t><<<nb, 256, 0, st>>>(d_sent_count.p, m, d_block_sums.p, p_dec_toff[k].p, d_sent_start.p,
+                                                          d_dec_tmp.p, p_dec_text[k].p, nullptr, nullptr, p_dec_text[k].cap, 0,
+                                                          text_base);
+    CUDA_TRY(cudaGetLastError());
+    launches += 3;
+    CUDA_TRY(cudaEventRecord(ev[3], st));
+    CUDA_TRY(cudaEventRecord(ev_out[k], st));
+    if (text_base + tot + 1 > h_dec_text.cap) {  // grow the pinned result buffer (rare): keep what has already arrived
+      CUDA_TRY(cudaStreamSynchronize(s_d2h));
+      PinBuf<char> bigger;
+      CUDA_TRY(bigger.ensure(static_cast<size_t>(static_cast<double>(text_base + tot) / static_cast<double>(hi) * 1.25 * n) + tot + 4096));
+      if (text_base) memcpy(bigger.p, h_dec_text.p, text_base);
+      h_dec_text.release();
+      h_dec_text = bigger;
+    }
+    CUDA_TRY(cudaStreamWaitEvent(s_d2h, ev_out[k], 0));
+    if (tot) CUDA_TRY(cudaMemcpyAsync(h_dec_text.p + text_base, p_dec_text[k].p, tot, cudaMemcpyDeviceToHost, s_d2h));
+    CUDA_TRY(cudaMemcpyAsync(h_dec_text_offsets.p + lo, p_dec_toff[k].p, (m + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, s_d2h));
+    CUDA_TRY(cudaEventRecord(ev_d2h[k], s_d2h));
+    text_base += tot;
+  }
+  CUDA_TRY(cudaStreamSynchronize(s_d2h));
+  if (trace) fprintf(stderr, "[trace] decode: text on host at %.3f ms (%zu chunks)\n", now_ms(), C);
+  {
+    float g = 0.f;
+    if (cudaEventElapsedTime(&g, ev[2], ev[3]) == cudaSuccess) all_ms += g;
+  }
+  h_dec_text.p[text_base] = 0;
+  last_launches = launches;
+  last_main_ms = main_ms;
+  last_ms = main_ms + all_ms;
+  last_h2d = total_ids * sizeof(int32_t) + (n + C) * sizeof(uint64_t);
+  last_d2h = text_base + (n + C) * sizeof(uint64_t);
+  *text = h_dec_text.p;
+  *text_offsets = h_dec_text_offsets.p;
+  return SPM_OK;
+}
+
 // ---- n-best (K5): lattice + A* per sentence on the GPU; leaves candidates in the temporary buffers ----
 int spm_engine::run_nbest(const char *bytes, const uint64_t *offsets, size_t n, uint32_t nbest, uint64_t *tmp_total) {
   cudaStream_t st = stream;
@@ -1601,14 +1811,16 @@ int spm_engine::run_nbest(const char *bytes, const uint64_t *offsets, size_t n, 
       grown = true;
       G.hyp_cap = std::min<uint32_t>(1u << 20, 8 * G.hyp_cap);
       G.node_cap = 65535u;
-      warps_per_cta = 2;
+      G.cap = std::max<uint32_t>(G.cap, 8192u);  // long sentences: text and per-position arrays in roomy slabs
+      warps_per_cta = G.hyp_cap > (1u << 17) ? 1 : 2;
       ctas = sm_count;
       warps_total = static_cast<size_t>(ctas) * warps_per_cta;
+      CUDA_TRY(d_lane_slabs.ensure(warps_total * lane_slab_bytes(G.cap) + 256));
       CUDA_TRY(d_nb_scratch.ensure(warps_total * 32 * nbest_lane_bytes(G) + 256));
       continue;
     }
     if (h_ctrl32.p[3]) {
-      set_error("n-best: a sentence exceeds the device path's capacity (normalized length > " + std::to_string(lane_cap) +
+      set_error("n-best: a sentence exceeds the device path's capacity (normalized length > " + std::to_string(G.cap) +
                 " bytes, lattice or hypothesis pool too large)");
       return SPM_ERR_UNSUPPORTED;
     }
@@ -1638,7 +1850,7 @@ int spm_engine::run_lattice(const char *bytes, const uint64_t *offsets, size_t n
   G.cap = lane_cap;
   G.node_cap = lane_cap * (trie.max_matches_per_start + 1) + 64;
   constexpr size_t kChunk = 32768;
-  const int warps_per_cta = 8;
+  int warps_per_cta = 8;
   last_launches = 0;
   last_h2d = last_d2h = 0;
   float main_ms = 0.f;
@@ -1655,9 +1867,9 @@ int spm_engine::run_lattice(const char *bytes, const uint64_t *offsets, size_t n
     CUDA_TRY(cudaMemcpyAsync(d_offsets.p, offsets + lo, (m + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     last_h2d += chunk_bytes + (m + 1) * sizeof(uint64_t);
     const size_t groups = (m + 31) / 32;
-    const int ctas = static_cast<int>(std::min<size_t>(sm_count, (groups + warps_per_cta - 1) / warps_per_cta));
-    const size_t warps_total = static_cast<size_t>(ctas) * warps_per_cta;
-    CUDA_TRY(d_lane_slabs.ensure(warps_total * lane_slab_bytes(lane_cap) + 256));
+    int ctas = static_cast<int>(std::min<size_t>(sm_count, (groups + warps_per_cta - 1) / warps_per_cta));
+    size_t warps_total = static_cast<size_t>(ctas) * warps_per_cta;
+    CUDA_TRY(d_lane_slabs.ensure(warps_total * lane_slab_bytes(G.cap) + 256));
     CUDA_TRY(d_lat_scratch.ensure(warps_total * 32 * lattice_lane_bytes(G) + 256));
     CUDA_TRY(d_lat_node_start.ensure(m));
     CUDA_TRY(d_lat_pos_start.ensure(m));
@@ -1701,8 +1913,20 @@ int spm_engine::run_lattice(const char *bytes, const uint64_t *offsets, size_t n
       CUDA_TRY(cudaStreamSynchronize(st));
       float a = 0.f;
       if (cudaEventElapsedTime(&a, ev[0], ev[1]) == cudaSuccess) main_ms += a;
+      if (h_ctrl32.p[3] && G.cap < 8192u) {
+        // a long sentence: this and the later chunks run with roomy per-lane slabs on fewer warps
+        G.cap = 8192u;
+        G.node_cap = G.cap * (trie.max_matches_per_start + 1) + 64;
+        warps_per_cta = 2;
+        ctas = static_cast<int>(std::min<size_t>(sm_count, (groups + warps_per_cta - 1) / warps_per_cta));
+        warps_total = static_cast<size_t>(ctas) * warps_per_cta;
+        CUDA_TRY(d_lane_slabs.ensure(warps_total * lane_slab_bytes(G.cap) + 256));
+        CUDA_TRY(d_lat_scratch.ensure(warps_total * 32 * lattice_lane_bytes(G) + 256));
+        --attempt;
+        continue;
+      }
       if (h_ctrl32.p[3]) {
-        set_error("lattice: a sentence exceeds the device path's capacity (normalized length > " + std::to_string(lane_cap) + " bytes)");
+        set_error("lattice: a sentence exceeds the device path's capacity (normalized length > " + std::to_string(G.cap) + " bytes)");
         return SPM_ERR_UNSUPPORTED;
       }
       if (h_ctrl32.p[2] && attempt == 0) { node_cap = h_ctrl64.p[0] + 1024; continue; }
@@ -1881,7 +2105,7 @@ void spm_engine_destroy(spm_engine *e) {
   if (e->stream) cudaStreamSynchronize(e->stream);
   e->d_link.release(); e->d_val.release(); e->d_user_link.release(); e->d_cm_units.release(); e->d_cm_lead.release();
   e->d_cm_pair.release(); e->d_id.release(); e->d_cm_solo.release(); e->d_byte_to_id.release(); e->d_cm_targets.release();
-  e->d_types.release(); e->d_scores.release(); e->d_word_safe.release(); e->d_word_fast.release(); e->d_kstats.release(); e->d_bytes.release(); e->d_tmp_norm.release(); e->d_norm.release();
+  e->d_types.release(); e->d_scores.release(); e->d_word_safe.release(); e->d_node4.release(); e->d_word_fast.release(); e->d_kstats.release(); e->d_bytes.release(); e->d_tmp_norm.release(); e->d_norm.release();
   e->d_long_scratch.release(); e->d_offsets.release(); e->d_tmp_ids.release(); e->d_ids.release();
   e->d_tmp_tok_end.release(); e->d_tok_end.release(); e->d_tmp_n2o.release(); e->d_n2o.release();
   e->d_sent_count.release(); e->d_norm_len.release(); e->d_deferred.release(); e->d_deferred2.release(); e->d_long_list.release();
@@ -1906,6 +2130,7 @@ void spm_engine_destroy(spm_engine *e) {
   e->s_bytes.release(); e->s_offsets.release(); e->d_ready.release(); e->h_marks.release(); e->h_progress.release();
   e->d_dec_off.release(); e->d_dec_info.release(); e->d_dec_bytes.release(); e->d_dec_tmp.release(); e->d_dec_text.release();
   e->d_dec_ids.release(); e->d_dec_text_offsets.release(); e->h_dec_text.release(); e->h_dec_text_offsets.release();
+  for (int k = 0; k < 2; ++k) { e->p_dec_ids[k].release(); e->p_dec_text[k].release(); e->p_dec_toff[k].release(); e->h_stage[k].release(); }
   e->d_order.release(); e->d_order_hist.release(); e->d_seg_done.release(); e->d_sent_rel.release(); e->d_seg_words.release();
   if (e->ev_offs) cudaEventDestroy(e->ev_offs);
   if (e->s_h2d) cudaStreamDestroy(e->s_h2d);
@@ -1958,6 +2183,7 @@ int spm_decode_ids(spm_engine *e, const int32_t *ids, const uint64_t *id_offsets
   }
   CUDA_TRY(cudaSetDevice(e->device));
   { const int rc = e->ensure_decode_tables(); if (rc) return rc; }
+  if (n >= e->pipeline_min_sentences) return e->decode_host_pipelined(ids, id_offsets, n, text, text_offsets);
   cudaStream_t st = e->stream;
   e->last_launches = 0;
   CUDA_TRY(e->h_dec_text_offsets.ensure(n + 1));

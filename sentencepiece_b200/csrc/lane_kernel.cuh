@@ -505,8 +505,8 @@ __global__ void __launch_bounds__(1024, 1) encode_unigram_lane_kernel(const KMod
     c.s_plain = s_tab + 8 + 1024 + 128;
     c.s_plainsp = c.s_plain + 4;
   }
-  const uint2 *node2 = M.trie_node2;
-  const uint32_t root = __ldg(&node2[0]).x;
+  const uint4 *node4 = M.trie_node4;
+  const uint32_t root = __ldg(&node4[0]).x;
   const bool bf = M.flags & kFlagByteFallback;
   const bool regular = M.flags & kFlagRegularScores;
   const bool fastwords = M.flags & kFlagFastWords;
@@ -542,7 +542,7 @@ __global__ void __launch_bounds__(1024, 1) encode_unigram_lane_kernel(const KMod
     // ---------------- K2: flat state machine, one trie transition per trip ----------------
     // text window: words w0..w3 = bytes [4*aw, 4*aw+16), aw = s >> 2; `cur` streams the bytes
     // from the walk position k (low byte first).  ss = ring slot of s, times 32.
-    uint32_t s = 0, ss = 0, k = 0, l = root, lv = 0, mblen = 1, nlog = 0;
+    uint32_t s = 0, ss = 0, k = 0, l = root, lsafe = 0, mblen = 1, nlog = 0;
     bool has_single = false, done = n == 0;
     bool wstart = true;  // s is the first character of a word (text start or U+2581)
     float base = 0.f;
@@ -586,11 +586,11 @@ __global__ void __launch_bounds__(1024, 1) encode_unigram_lane_kernel(const KMod
             cur >>= 8;
           }
           const uint32_t v = (l >> kLinkBaseShift) ^ ch;
-          const uint2 nd = __ldg(&node2[v]);  // {link, child mask}: one 8-byte load (L1/L2)
+          const uint4 nd = __ldg(&node4[v]);  // {link, child mask, score, word_safe}: one 16-byte load (L1/L2)
           if ((nd.x & kLinkLabelMask) == ch) {
             ++k;
             l = nd.x;
-            lv = v;
+            lsafe = nd.w;
             const uint32_t kind = (nd.x >> kLinkKindShift) & 3u;
             if (kind == kKindNormal || kind == kKindUserDefined) {
               const uint32_t plen = k - s;
@@ -605,14 +605,14 @@ __global__ void __launch_bounds__(1024, 1) encode_unigram_lane_kernel(const KMod
                 // |score|, |base| in {0} U [2^-10, 2^18) the double sum a + b is exact, so
                 // (float)cand == fl(a + b) and cand > cur <=> ns > cur || (ns == cur && err > 0),
                 // err being the exact rounding error of the float add (Knuth two-sum).
-                const float a = __uint_as_float(__ldg(M.trie_val + v));
+                const float a = __uint_as_float(nd.z);
                 ns = __fadd_rn(a, base);
                 const float bb = __fsub_rn(ns, a);
                 const float err = __fadd_rn(__fsub_rn(a, __fsub_rn(ns, bb)), __fsub_rn(base, bb));
                 better = unset || ns > curs || (ns == curs && err > 0.f);
               } else {
                 const double sc = kind == kKindNormal
-                                      ? static_cast<double>(__uint_as_float(__ldg(M.trie_val + v)))
+                                      ? static_cast<double>(__uint_as_float(nd.z))
                                       : static_cast<double>(__fmul_rn(static_cast<float>(plen), M.max_score)) - 0.1;
                 const double cand = sc + static_cast<double>(base);
                 better = unset || cand > static_cast<double>(curs);
@@ -657,7 +657,7 @@ __global__ void __launch_bounds__(1024, 1) encode_unigram_lane_kernel(const KMod
               }
               wend = b3 == kWsWord;
             }
-            fast = wend && k <= static_cast<uint32_t>(__ldg(M.word_safe + lv));
+            fast = wend && k <= lsafe;
           }
           const uint32_t s_old = s;
           uint32_t steplog;
@@ -696,6 +696,10 @@ __global__ void __launch_bounds__(1024, 1) encode_unigram_lane_kernel(const KMod
             if (jw == 1u) {
               w0 = w1; w1 = w2; w2 = w3;
               w3 = c.text_w[static_cast<size_t>((s >> 2) + 3) * 32];
+            } else if (jw == 2u) {
+              w0 = w2; w1 = w3;
+              w2 = c.text_w[static_cast<size_t>((s >> 2) + 2) * 32];
+              w3 = c.text_w[static_cast<size_t>((s >> 2) + 3) * 32];
             } else if (jw != 0u) {
               const uint32_t *tw = c.text_w + static_cast<size_t>(s >> 2) * 32;
               w0 = tw[0]; w1 = tw[32]; w2 = tw[64]; w3 = tw[96];
@@ -726,7 +730,7 @@ __global__ void __launch_bounds__(1024, 1) encode_unigram_lane_kernel(const KMod
       }
     }
     lane_finish(M, B, c, n, nlog, lane, have, defer, sent, bf);  // K4
-    lane_drain(B, first, lane);  // K6 (fused host path only)
+    lane_drain(B, sent, have, lane);  // K6 (fused host path only)
     __syncwarp();
   }
 }

@@ -190,7 +190,10 @@ class SentencePieceProcessor:
 
     # sentencepiece_processor.h:261
     def LoadFromSerializedProto(self, serialized, device=0):
-        self._engine = Engine(bytes(serialized), device=device)
+        self._model_bytes = bytes(serialized)
+        self._engine = Engine(self._model_bytes, device=device)
+        self._pieces = None
+        self._unk_id = -1
         return True
 
     def _require(self):
@@ -220,12 +223,72 @@ class SentencePieceProcessor:
         out = [ids[int(ido[i]):int(ido[i + 1])].tolist() for i in range(len(offs) - 1)]
         return out[0] if single else out
 
-    def encode(self, input, out_type=int):
-        if out_type is not int:
-            raise NotImplementedError("use the C++ host layer for piece output")
-        return self.EncodeAsIds(input)
+    # ---- pieces: ids + token ends in the normalized text (spm_encode_spans); unknown tokens keep their surface
+    #      (sentencepiece_processor.cc:609-621) ----
+    def EncodeAsPieces(self, input):
+        self._require()
+        single = isinstance(input, (str, bytes))
+        buf, offs = pack_sentences([input] if single else input)
+        r = self._engine.encode_spans(buf, offs)
+        if self._pieces is None:
+            from . import _modelinfo
+            self._pieces, self._unk_id = _modelinfo.pieces_and_unk(self._model_bytes)
+        ids, te, ido, no, norm = r["ids"], r["tok_end"], r["id_offsets"], r["norm_offsets"], r["normalized"]
+        out = []
+        for i in range(len(offs) - 1):
+            base, begin, row = int(no[i]), 0, []
+            for k in range(int(ido[i]), int(ido[i + 1])):
+                end = int(te[k])
+                if int(ids[k]) == self._unk_id:
+                    row.append(norm[base + begin:base + end].decode("utf-8", errors="replace"))
+                else:
+                    row.append(self._pieces[int(ids[k])])
+                begin = end
+            out.append(row)
+        return out[0] if single else out
+
+    def encode(self, input, out_type=int, enable_sampling=False, nbest_size=-1, alpha=0.1):
+        """python/src/sentencepiece/__init__.py Encode: out_type int | str; enable_sampling uses SampleEncode."""
+        if enable_sampling:
+            if out_type is not int:
+                raise NotImplementedError("sampled pieces: use the C++ host layer (SampleEncodeAsPieces)")
+            return self.SampleEncodeAsIds(input, nbest_size, alpha)
+        return self.EncodeAsIds(input) if out_type is int else self.EncodeAsPieces(input)
 
     Encode = encode
+
+    def _split(self, input):
+        single = isinstance(input, (str, bytes))
+        return single, pack_sentences([input] if single else input)
+
+    # sentencepiece_processor.h:481; the draws of a batch are taken in order on one generator (SetRandomGeneratorSeed)
+    def SampleEncodeAsIds(self, input, nbest_size, alpha):
+        self._require()
+        single, (buf, offs) = self._split(input)
+        ids, ido = self._engine.sample_encode(buf, offs, nbest_size, alpha)
+        out = [ids[int(ido[i]):int(ido[i + 1])].tolist() for i in range(len(offs) - 1)]
+        return out[0] if single else out
+
+    # sentencepiece_processor.h:471
+    def NBestEncodeAsIds(self, input, nbest_size):
+        self._require()
+        single, (buf, offs) = self._split(input)
+        r = self._engine.nbest_encode(buf, offs, nbest_size)
+        K, co = r["K"], r["cand_offsets"]
+        out = [[r["ids"][int(co[i * K + c]):int(co[i * K + c + 1])].tolist() for c in range(int(r["n_cands"][i]))]
+               for i in range(len(offs) - 1)]
+        return out[0] if single else out
+
+    # sentencepiece_processor.h:521-526
+    def CalculateEntropy(self, input, alpha):
+        self._require()
+        single, (buf, offs) = self._split(input)
+        ent = self._engine.calculate_entropy(buf, offs, alpha).tolist()
+        return ent[0] if single else ent
+
+    def SetRandomGeneratorSeed(self, seed):
+        self._require()
+        self._engine.set_random_seed(seed)
 
     @property
     def engine(self):

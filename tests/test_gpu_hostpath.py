@@ -104,3 +104,44 @@ def test_large_batch_rejects_decreasing_offsets(corpus_gen):
     a, ao = eng.encode_packed(buf, offs)  # the engine is still usable
     assert len(ao) == N + 1 and int(ao[-1]) == len(a)
     eng.close()
+
+
+@pytest.mark.parametrize("model,kind", [("uni32k", "en"), ("mix_bf8k", "mixed")])
+def test_decode_pipelined_equals_plain(model, kind, corpus_gen):
+    """spm_decode_ids on >= 300k lists takes the chunked three-stage pipeline (staged H2D of pageable ids, decode,
+    D2H of the text); the same lists in two halves take the plain path.  Both must agree, pageable and pinned input
+    alike, and match the live reference / the oracle on a sample."""
+    import ctypes
+    buf, offs = corpus_gen.fill(kind, 7005, N)
+    eng = _engine(model)
+    ids, ido = eng.encode_packed(buf, offs)
+    text, to = eng.decode_packed(ids, ido)                    # pageable numpy arrays -> staged
+    h = N // 3                                                # < 300k lists: plain path
+    parts, base = [], 0
+    for lo, hi in ((0, h), (h, 2 * h), (2 * h, N)):
+        t, o = eng.decode_packed(ids, ido[lo:hi + 1])
+        assert int(o[0]) == 0
+        assert np.array_equal(o + np.uint64(base), to[lo:hi + 1]), (lo, hi)
+        parts.append(t)
+        base += int(o[-1])
+    assert np.array_equal(np.concatenate(parts), text)
+    # pinned input goes straight to the copy engine
+    lib = eng._lib
+    p_ids = lib.spm_host_alloc(ids.nbytes + 64)
+    pin = np.ctypeslib.as_array(ctypes.cast(p_ids, ctypes.POINTER(ctypes.c_int32)), (ids.size,))
+    pin[:] = ids
+    t2, o2 = eng.decode_packed(pin, ido)
+    lib.spm_host_free(p_ids)
+    assert np.array_equal(o2, to) and np.array_equal(t2, text)
+    om = oracle_py.OracleModel(model_bytes(model))
+    k = 3000
+    ot, oto = om.decode_batch(ids[: int(ido[k])], ido[: k + 1])
+    assert np.array_equal(oto, to[: k + 1]) and np.array_equal(ot, text[: int(to[k])])
+    # an id out of range fails the call like the reference (sentencepiece_processor.cc:915-918), also mid-pipeline
+    bad = ids.copy()
+    bad[int(ido[N - 5])] = 10 ** 8
+    with pytest.raises(RuntimeError, match="Invalid id"):
+        eng.decode_packed(bad, ido)
+    t3, o3 = eng.decode_packed(ids, ido)                      # and the engine is usable afterwards
+    assert np.array_equal(o3, to) and np.array_equal(t3, text)
+    eng.close()

@@ -103,3 +103,55 @@ def test_nbest_error_behaviour(corpus_gen):
     with pytest.raises(RuntimeError, match="CalculateEntropy is not available"):
         bpe.calculate_entropy(buf, offs, 0.5)
     bpe.close()
+
+
+@pytest.mark.parametrize("nbest", [512, 1024])
+def test_nbest_large(nbest, corpus_gen):
+    """nbest 512 / 1024 (the clamp of unigram_model.cc:701): on ~130-byte sentences the agenda passes 10,000 entries and
+    is shrunk to min(512, 10 * nbest) (:481-505); hypothesis pools overflow the first attempt's capacity and the batch is
+    redone with roomy slabs."""
+    lines = corpus_gen.lines("en", 8106, 24) + [b"a", b""]
+    buf, offs = oracle_py.pack(lines)
+    eng = _engine("uni32k")
+    r = eng.nbest_encode(buf, offs, nbest)
+    om = oracle_py.OracleModel(model_bytes("uni32k"))
+    K = r["K"]
+    assert K == nbest
+    for i, s in enumerate(lines):
+        cands, scores = om.nbest_encode(s, nbest)
+        assert int(r["n_cands"][i]) == len(cands), i
+        for c, (ids, sc) in enumerate(zip(cands, scores)):
+            a, b = int(r["cand_offsets"][i * K + c]), int(r["cand_offsets"][i * K + c + 1])
+            assert r["ids"][a:b].tolist() == ids.tolist(), (i, c)
+            assert np.float32(r["scores"][i * K + c]).view(np.uint32) == np.float32(sc).view(np.uint32), (i, c)
+    eng.close()
+
+
+def test_nbest_and_sampling_long_sentences(corpus_gen):
+    """Sentences beyond the 512 normalized bytes of the fast slabs (up to ~8 KB) are redone with roomy slabs instead of
+    being refused: n-best lists, seeded n-best sampling and seeded lattice sampling against the oracle."""
+    short = corpus_gen.lines("en", 8107, 40)
+    long1 = b" ".join(corpus_gen.lines("en", 8108, 12))            # ~1.6 KB
+    long2 = " ".join(l.decode("utf8", "replace") for l in corpus_gen.lines("mixed", 8109, 10)).encode()
+    lines = short[:20] + [long1] + short[20:] + [long2, b"x"]
+    buf, offs = oracle_py.pack(lines)
+    assert max(len(x) for x in lines) > 1500
+    eng = _engine("uni32k")
+    om = oracle_py.OracleModel(model_bytes("uni32k"))
+    r = eng.nbest_encode(buf, offs, 8)
+    K = r["K"]
+    for i, s in enumerate(lines):
+        cands, scores = om.nbest_encode(s, 8)
+        assert int(r["n_cands"][i]) == len(cands), i
+        for c, (ids, sc) in enumerate(zip(cands, scores)):
+            a, b = int(r["cand_offsets"][i * K + c]), int(r["cand_offsets"][i * K + c + 1])
+            assert r["ids"][a:b].tolist() == ids.tolist(), (i, c)
+            assert np.float32(r["scores"][i * K + c]).view(np.uint32) == np.float32(sc).view(np.uint32), (i, c)
+    for nb in (8, -1):
+        eng.set_random_seed(31337)
+        ids, ido = eng.sample_encode(buf, offs, nb, 0.3)
+        oids, oido = om.sample_encode_batch(buf, offs, nb, 0.3, 31337)
+        assert np.array_equal(ido, oido) and np.array_equal(ids, oids), nb
+    ent = eng.calculate_entropy(buf, offs, 0.3)
+    np.testing.assert_allclose(ent, om.entropy_batch(buf, offs, 0.3), rtol=2e-5, atol=2e-5)
+    eng.close()
