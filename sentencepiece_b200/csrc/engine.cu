@@ -209,6 +209,14 @@ struct spm_engine {
     int threads = 0;
     uint32_t R = 0, smem = 0;
   };
+  // unigram: which instantiation takes the next batch -- the whole-word shortcut pays on text made of space-separated
+  // words and only costs on text without them (CJK, mixed script).  Decided per call from a sample of the batch's bytes
+  // (pick_fast_words); SPM_B200_FASTWORDS=0/1 forces it.
+  bool batch_fast_words = true;
+  int force_fast_words = -1;
+  DevBuf<unsigned long long> d_sample;
+  bool pick_fast_words_host(const char *bytes, const uint64_t *offsets, size_t n) const;
+  int pick_fast_words_device(const uint8_t *d_bytes_base, const uint64_t *d_offs, size_t n, cudaStream_t st, bool *fast);
   bool any_user_defined = false;
   LaneGeom lane_geometry() const {
     LaneGeom g;
@@ -228,7 +236,8 @@ struct spm_engine {
     }
     if (trie.max_key_len > 62) return g;
     g.R = trie.max_key_len + 2;
-    const size_t ring = lane_ring_bytes(g.R);
+    g.version = ((km.flags & kFlagFastWords) && batch_fast_words) ? 2 : 1;  // 2: whole-word shortcut, 1: plain
+    const size_t ring = g.version == 2 ? lane_ring_bytes(g.R) : static_cast<size_t>(g.R) * 32 * 8;
     const int warps = static_cast<int>(std::min<size_t>(threads / 32, avail / ring));
     if (warps < 4) return g;
     g.ok = true;
@@ -726,6 +735,7 @@ int spm_engine::configure_kernel_attrs() {
   CUDA_TRY(set_smem(encode_unigram_long_kernel<false>, mx));
   CUDA_TRY(set_smem(encode_unigram_long_kernel<true>, mx));
   CUDA_TRY(set_smem(encode_unigram_lane_kernel, mx));
+  CUDA_TRY(set_smem(encode_unigram_lane_plain_kernel, mx));
   CUDA_TRY(set_smem(encode_bpe_lane_kernel, mx));
   CUDA_TRY(set_smem(encode_bpe_lane2_kernel, mx));
   CUDA_TRY(set_smem(nbest_lane_kernel<kNbestTop, 1024>, mx));
@@ -736,6 +746,40 @@ int spm_engine::configure_kernel_attrs() {
   CUDA_TRY(set_smem(encode_bpe_kernel<true>, mx));
   CUDA_TRY(set_smem(encode_bpe_long_kernel<false>, mx));
   CUDA_TRY(set_smem(encode_bpe_long_kernel<true>, mx));
+  return SPM_OK;
+}
+
+// Which instantiation of the unigram lane kernel takes this batch: the whole-word shortcut wants text made of
+// space-separated words.  A sample of the batch's bytes decides (one space per <= 16 bytes: words of <= 15 bytes on
+// average); results never depend on the choice, only the speed does.
+bool spm_engine::pick_fast_words_host(const char *bytes, const uint64_t *offsets, size_t n) const {
+  if (force_fast_words >= 0) return force_fast_words != 0;
+  if (!(km.flags & kFlagFastWords) || !bytes || n == 0) return true;
+  const uint64_t lo = offsets[0], hi = offsets[n];
+  if (hi <= lo + 64) return true;
+  const uint64_t total = hi - lo, win = std::min<uint64_t>(total, 4096);
+  uint64_t spaces = 0, seen = 0;
+  for (int w = 0; w < 16; ++w) {
+    const uint64_t start = lo + (total - win) * static_cast<uint64_t>(w) / 15;
+    for (uint64_t k = 0; k < win; ++k) spaces += bytes[start + k] == ' ';
+    seen += win;
+  }
+  return spaces * 16 >= seen;
+}
+
+int spm_engine::pick_fast_words_device(const uint8_t *d_bytes_base, const uint64_t *d_offs, size_t n, cudaStream_t st, bool *fast) {
+  *fast = true;
+  if (force_fast_words >= 0) { *fast = force_fast_words != 0; return SPM_OK; }
+  if (!(km.flags & kFlagFastWords) || n == 0) return SPM_OK;
+  CUDA_TRY(d_sample.ensure(2));
+  CUDA_TRY(h_ctrl64.ensure(8));
+  CUDA_TRY(cudaMemsetAsync(d_sample.p, 0, 2 * sizeof(unsigned long long), st));
+  sample_spaces_kernel<<<16, 256, 0, st>>>(d_bytes_base, d_offs, static_cast<uint32_t>(n), d_sample.p);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(h_ctrl64.p + 6, d_sample.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  const unsigned long long spaces = h_ctrl64.p[6], seen = h_ctrl64.p[7];
+  *fast = seen < 64 || spaces * 16 >= seen;
   return SPM_OK;
 }
 
@@ -795,7 +839,8 @@ int spm_engine::run_device(const uint8_t *d_bytes_base, const uint64_t *d_offs, 
   }
   if (lane_path || bpe_lane_path) {
     geom.tiles = lg.threads / 32;
-    geom.tile_bytes = bpe ? (lg.version == 2 ? kBpeLane2WarpBytes : kBpeLaneWarpBytes) : lane_ring_bytes(lg.R);
+    geom.tile_bytes = bpe ? (lg.version == 2 ? kBpeLane2WarpBytes : kBpeLaneWarpBytes)
+                          : (lg.version == 2 ? lane_ring_bytes(lg.R) : lg.R * 32 * 8);
     geom.hot_link = geom.hot_val = 0;  // the lane kernels read the trie through L1: rings / word arrays get the shared memory
     geom.smem_bytes = lg.smem;
     const size_t warps_total = static_cast<size_t>(sm_count) * ctas_per_sm * geom.tiles;
@@ -878,8 +923,10 @@ int spm_engine::run_device(const uint8_t *d_bytes_base, const uint64_t *d_offs, 
     } else if (bpe) {
       if (spans) encode_bpe_kernel<true><<<grid, tile_threads, geom.smem_bytes, st>>>(M, B);
       else encode_bpe_kernel<false><<<grid, tile_threads, geom.smem_bytes, st>>>(M, B);
-    } else if (lane_path) {
+    } else if (lane_path && lg.version == 2) {
       encode_unigram_lane_kernel<<<grid, lg.threads, geom.smem_bytes, st>>>(M, B, d_lane_slabs.p, lane_cap, lg.R);
+    } else if (lane_path) {
+      encode_unigram_lane_plain_kernel<<<grid, lg.threads, geom.smem_bytes, st>>>(M, B, d_lane_slabs.p, lane_cap, lg.R);
     } else if (warp_path) {
       if (threads <= 512) encode_unigram_warp_kernel<512><<<grid, threads, geom.smem_bytes, st>>>(M, B);
       else encode_unigram_warp_kernel<1024><<<grid, threads, geom.smem_bytes, st>>>(M, B);
@@ -1432,13 +1479,19 @@ int spm_engine::encode_host_fused(const char *bytes, const uint64_t *offsets, si
   B.out_off_base = 0;
   B.kstats = trace ? d_ctrl64.p + 4 : nullptr;
   CUDA_TRY(cudaEventRecord(ev[0], st));
-  // processing order: sorted over whole input pieces (the unit in which the bytes arrive); compaction works on the much
-  // smaller drain segments, whose completion is counted per sentence (drain.cuh)
-  { const int rc = build_order(s_offsets.p, n, st, &B.order, 1u << kPieceShift); if (rc) return rc; }
+  // processing order: sorted within blocks of 2^sort_shift sentences (drain segment <= block <= input piece); the
+  // completion of a drain segment is counted per sentence (drain.cuh), so the two granularities are independent.
+  // Measured (profiles/README.md): sorting whole pieces makes all 32 segments of a piece finish in the same last few
+  // groups, whose warps then compact them one after the other -- e2e 192 -> 81 M sentences/s; the default stays at
+  // the segment size.
+  uint32_t sort_shift = kSegShift;
+  if (const char *v = getenv("SPM_B200_SORT_SHIFT")) sort_shift = std::min<uint32_t>(kPieceShift, std::max<uint32_t>(kSegShift, atoi(v)));
+  { const int rc = build_order(s_offsets.p, n, st, &B.order, 1u << sort_shift); if (rc) return rc; }
   if (!B.order) { set_error("fused path needs the segment order"); return SPM_ERR_ARG; }
   if (bpe && lg.version == 2) encode_bpe_lane2_kernel<<<grid, lane_threads, smem, st>>>(M, B, d_lane_slabs.p, lane_cap);
   else if (bpe) encode_bpe_lane_kernel<<<grid, lane_threads, smem, st>>>(M, B, d_lane_slabs.p, lane_cap);
-  else encode_unigram_lane_kernel<<<grid, lane_threads, smem, st>>>(M, B, d_lane_slabs.p, lane_cap, lg.R);
+  else if (lg.version == 2) encode_unigram_lane_kernel<<<grid, lane_threads, smem, st>>>(M, B, d_lane_slabs.p, lane_cap, lg.R);
+  else encode_unigram_lane_plain_kernel<<<grid, lane_threads, smem, st>>>(M, B, d_lane_slabs.p, lane_cap, lg.R);
   CUDA_TRY(cudaGetLastError());
   ++last_launches;
   CUDA_TRY(cudaEventRecord(ev[1], st));
@@ -2044,7 +2097,7 @@ static int create_common(spm_engine *e, int device, spm_engine **out) {
   e->sm_count = prop.multiProcessorCount;
   if (const char *v = getenv("SPM_B200_SORT")) e->sort_by_length = atoi(v) != 0;  // A/B knob for profiles/
   if (const char *v = getenv("SPM_B200_FUSED")) e->fused_host_path = atoi(v) != 0;
-  if (const char *v = getenv("SPM_B200_FASTWORDS")) e->fast_words = atoi(v) != 0;
+  if (const char *v = getenv("SPM_B200_FASTWORDS")) e->force_fast_words = atoi(v) != 0 ? 1 : 0;
   if (const char *v = getenv("SPM_B200_KSTATS")) e->kstats = atoi(v) != 0;
   if (const char *v = getenv("SPM_B200_BPE_LANE_V")) e->bpe_lane_version = atoi(v);
   e->smem_optin = prop.sharedMemPerBlockOptin;
@@ -2105,7 +2158,7 @@ void spm_engine_destroy(spm_engine *e) {
   if (e->stream) cudaStreamSynchronize(e->stream);
   e->d_link.release(); e->d_val.release(); e->d_user_link.release(); e->d_cm_units.release(); e->d_cm_lead.release();
   e->d_cm_pair.release(); e->d_id.release(); e->d_cm_solo.release(); e->d_byte_to_id.release(); e->d_cm_targets.release();
-  e->d_types.release(); e->d_scores.release(); e->d_word_safe.release(); e->d_node4.release(); e->d_word_fast.release(); e->d_kstats.release(); e->d_bytes.release(); e->d_tmp_norm.release(); e->d_norm.release();
+  e->d_types.release(); e->d_scores.release(); e->d_word_safe.release(); e->d_node4.release(); e->d_word_fast.release(); e->d_kstats.release(); e->d_sample.release(); e->d_bytes.release(); e->d_tmp_norm.release(); e->d_norm.release();
   e->d_long_scratch.release(); e->d_offsets.release(); e->d_tmp_ids.release(); e->d_ids.release();
   e->d_tmp_tok_end.release(); e->d_tok_end.release(); e->d_tmp_n2o.release(); e->d_n2o.release();
   e->d_sent_count.release(); e->d_norm_len.release(); e->d_deferred.release(); e->d_deferred2.release(); e->d_long_list.release();
@@ -2353,6 +2406,10 @@ int spm_encode_ids_device(spm_engine *e, const char *d_bytes, const uint64_t *d_
     return SPM_OK;
   }
   e->last_h2d = e->last_d2h = 0;
+  if (e->model.model_type == SPM_UNIGRAM) {
+    const int rc0 = e->pick_fast_words_device(reinterpret_cast<const uint8_t *>(d_bytes), d_offsets, n, st, &e->batch_fast_words);
+    if (rc0) return rc0;
+  }
   const int rc = e->run_device(reinterpret_cast<const uint8_t *>(d_bytes), d_offsets, n, total_bytes, false, d_ids,
                                ids_capacity, reinterpret_cast<unsigned long long *>(d_id_offsets), total_ids, nullptr, st);
   if (rc) return rc;
@@ -2430,6 +2487,8 @@ static int encode_host_locked(spm_engine *e, const char *bytes, const uint64_t *
 // spm_encode_ids with e->mu already held (also used by the n-best / sampling entry points for nbest_size <= 1)
 static int encode_ids_locked(spm_engine *e, const char *bytes, const uint64_t *offsets, size_t n, const int32_t **ids,
                              const uint64_t **id_offsets) {
+  if (offsets && bytes && e->model.model_type == SPM_UNIGRAM && n < 0xFFFFFFF0ull && offsets[n] >= offsets[0])
+    e->batch_fast_words = e->pick_fast_words_host(bytes, offsets, n);
   if (offsets && ids && id_offsets && bytes && n >= e->pipeline_min_sentences && n < 0xFFFFFFF0ull) {
     if (e->uses_lane_kernel() && e->sort_by_length && e->fused_host_path) {
       if (e->fused_skip > 0) --e->fused_skip;

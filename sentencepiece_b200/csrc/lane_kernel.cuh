@@ -735,5 +735,202 @@ __global__ void __launch_bounds__(1024, 1) encode_unigram_lane_kernel(const KMod
   }
 }
 
+// The same kernel without the whole-word shortcut: the round-1 state machine (8-byte {link, child mask} nodes, score
+// lookup on a match, cleared ring slots instead of position tags).  Text with few space-separated words -- CJK, the
+// byte-fallback / mixed-script configuration -- gains nothing from the shortcut and would only pay for its bookkeeping
+// (7.6 vs 6.5 ms per 1M mixed sentences), so the engine picks this instantiation for such batches (engine.cu,
+// `pick_fast_words`); ring geometry R * 32 * 8 bytes per warp.
+__global__ void __launch_bounds__(1024, 1) encode_unigram_lane_plain_kernel(const KModel M, const KBatch B, uint8_t *slabs,
+                                                                       uint32_t cap, uint32_t R) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint32_t *s_tab = reinterpret_cast<uint32_t *>(smem);
+  uint8_t *rings = smem + kLaneTableBytes;
+  fill_lane_tables(M, s_tab);
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warp_in_cta = threadIdx.x >> 5;
+  const uint32_t warp_global = blockIdx.x * (blockDim.x >> 5) + warp_in_cta;
+  LaneCtx c;
+  {
+    uint8_t *ring = rings + static_cast<size_t>(warp_in_cta) * (R * 32 * 8);
+    c.rs = reinterpret_cast<float *>(ring) + lane;
+    c.rb = reinterpret_cast<uint32_t *>(ring + R * 32 * 4) + lane;
+    uint8_t *slab = slabs + static_cast<size_t>(warp_global) * lane_slab_bytes(cap);
+    c.text_w = reinterpret_cast<uint32_t *>(slab) + lane;
+    c.log = reinterpret_cast<uint32_t *>(slab) + static_cast<size_t>(cap / 4 + kLaneTextSlack) * 32 + lane;
+    c.s_lead = s_tab;
+    c.s_pair = s_tab + 8;
+    c.s_solo = reinterpret_cast<const int32_t *>(s_tab + 8 + 1024);
+    c.s_plain = s_tab + 8 + 1024 + 128;
+    c.s_plainsp = c.s_plain + 4;
+  }
+  const uint2 *node2 = M.trie_node2;
+  const uint32_t root = __ldg(&node2[0]).x;
+  const bool bf = M.flags & kFlagByteFallback;
+  const bool regular = M.flags & kFlagRegularScores;
+
+  for (;;) {
+    uint32_t first = 0;
+    if (lane == 0) first = atomicAdd(B.work_counter, 32u);
+    first = __shfl_sync(0xFFFFFFFFu, first, 0);
+    if (first >= B.n) break;
+    lane_wait_input(B, first, lane);
+    const bool have = first + lane < B.n;
+    const uint32_t sent = have && B.order ? B.order[first + lane] : first + lane;
+    // ---------------- K1 ----------------
+    uint32_t n = 0;
+    bool defer = false;
+    if (have) {
+      const unsigned long long off = B.offsets[sent];
+      const unsigned long long len64 = B.offsets[sent + 1] - off;
+      if (len64 > 4ull * cap || off < B.off_lo || off + len64 > B.off_hi) defer = true;
+      else {
+        n = lane_normalize(M, B.bytes + off, static_cast<uint32_t>(len64), c, cap);
+        if (n == 0xFFFFFFFFu) { defer = true; n = 0; }
+      }
+      if (defer) {
+        const uint32_t slot = atomicAdd(B.status, 1u);
+        B.deferred[2 * slot] = sent;
+        B.deferred[2 * slot + 1] = 0;
+        B.sent_count[sent] = 0;  // until a later pass encodes it
+      }
+    }
+    __syncwarp();
+    // ---------------- K2: flat state machine, one trie transition per trip ----------------
+    // text window: words w0..w3 = bytes [4*aw, 4*aw+16), aw = s >> 2; `cur` streams the bytes
+    // from the walk position k (low byte first).
+    uint32_t s = 0, ss = 0 /* ring slot of s */, k = 0, l = root, mblen = 1, nlog = 0;
+    bool has_single = false, done = n == 0;
+    float base = 0.f;
+    bool base_regular = regular;  // base == 0
+    uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+    unsigned long long cur = 0;
+    auto window_low = [&]() -> unsigned long long {  // bytes s .. s+7
+      const uint32_t sh = (s & 3u) * 8u;
+      return static_cast<unsigned long long>(__funnelshift_r(w0, w1, sh)) |
+             (static_cast<unsigned long long>(__funnelshift_r(w1, w2, sh)) << 32);
+    };
+    auto window_high = [&]() -> unsigned long long {  // bytes s+8 .. (at least s+12)
+      const uint32_t sh = (s & 3u) * 8u;
+      return static_cast<unsigned long long>(__funnelshift_r(w2, w3, sh)) |
+             (static_cast<unsigned long long>(w3 >> sh) << 32);
+    };
+    if (!done) {
+      for (uint32_t r = 0; r < R; ++r) c.rb[r * 32] = 0u;  // all positions unset
+      c.rs[0] = 0.f;
+      w0 = c.text_w[0]; w1 = c.text_w[32]; w2 = c.text_w[64]; w3 = c.text_w[96];
+      mblen = one_char_len(w0 & 0xFFu);
+      if (mblen > n) mblen = n;
+      cur = window_low();
+    }
+    while (__any_sync(0xFFFFFFFFu, !done)) {
+      if (!done) {
+        bool end_walk = true;
+        if (k < n) {
+          const uint32_t d = k - s;
+          uint32_t ch;
+          if (d >= 13u) {  // beyond the register window: long piece, rare
+            ch = (c.text_w[static_cast<size_t>(k >> 2) * 32] >> ((k & 3u) * 8u)) & 0xFFu;
+          } else {
+            if (d == 8u) cur = window_high();
+            ch = static_cast<uint32_t>(cur) & 0xFFu;
+            cur >>= 8;
+          }
+          const uint32_t v = (l >> kLinkBaseShift) ^ ch;
+          const uint2 nd = __ldg(&node2[v]);  // {link, child mask}: one 8-byte load (L1/L2)
+          if ((nd.x & kLinkLabelMask) == ch) {
+            ++k;
+            l = nd.x;
+            const uint32_t kind = (nd.x >> kLinkKindShift) & 3u;
+            if (kind == kKindNormal || kind == kKindUserDefined) {
+              const uint32_t plen = k - s;
+              uint32_t sl = ss + plen;
+              if (sl >= R) sl -= R;
+              sl *= 32;
+              const float curs = c.rs[sl];
+              const bool unset = c.rb[sl] == 0u;
+              float ns;
+              bool better;
+              if (kind == kKindNormal && base_regular) {
+                // Exact float formulation of the reference's double comparison (Q1).  With
+                // |score|, |base| in {0} U [2^-10, 2^18) the double sum a + b is exact, so
+                // (float)cand == fl(a + b) and cand > cur <=> ns > cur || (ns == cur && err > 0),
+                // err being the exact rounding error of the float add (Knuth two-sum).
+                const float a = __uint_as_float(__ldg(M.trie_val + v));
+                ns = __fadd_rn(a, base);
+                const float bb = __fsub_rn(ns, a);
+                const float err = __fadd_rn(__fsub_rn(a, __fsub_rn(ns, bb)), __fsub_rn(base, bb));
+                better = unset || ns > curs || (ns == curs && err > 0.f);
+              } else {
+                const double sc = kind == kKindNormal
+                                      ? static_cast<double>(__uint_as_float(__ldg(M.trie_val + v)))
+                                      : static_cast<double>(__fmul_rn(static_cast<float>(plen), M.max_score)) - 0.1;
+                const double cand = sc + static_cast<double>(base);
+                better = unset || cand > static_cast<double>(curs);
+                ns = static_cast<float>(cand);
+              }
+              if (better) {
+                c.rs[sl] = ns;
+                c.rb[sl] = (plen << 24) | v;
+              }
+              has_single |= plen == mblen;
+            }
+            // early termination: if the node has no child on the next byte the failing
+            // probe (and its cold miss) is skipped and the start transition happens now
+            if (k < n) {
+              uint32_t nb;
+              const uint32_t d2 = k - s;
+              if (d2 >= 13u) nb = (c.text_w[static_cast<size_t>(k >> 2) * 32] >> ((k & 3u) * 8u)) & 0xFFu;
+              else nb = d2 == 8u ? static_cast<uint32_t>(window_high()) & 0xFFu : static_cast<uint32_t>(cur) & 0xFFu;
+              end_walk = !((nd.y >> (nb & 31u)) & 1u);
+            }
+          }
+        }
+        if (end_walk) {
+          // the walk from s is over (traverse() == -2, or end of text)
+          uint32_t sl = ss + mblen;
+          if (sl >= R) sl -= R;
+          if (!has_single) {  // UNK edge, unigram_model.cc:995-1005
+            const float cand = __fadd_rn(M.unk_score, base);
+            if (c.rb[sl * 32] == 0u || cand > c.rs[sl * 32]) {
+              c.rs[sl * 32] = cand;
+              c.rb[sl * 32] = (mblen << 24) | kLaneUnk;
+            }
+          }
+          // position s leaves the window; only character starts are ever targets, so its
+          // slot is the only one that has to be cleared for position s + R
+          c.rb[ss * 32] = 0u;
+          s += mblen;
+          ss = sl;
+          // position s is final: append (plen | previous char length | unit) to the log
+          c.log[static_cast<size_t>(nlog) * 32] = c.rb[ss * 32] | ((mblen - 1u) << 22);
+          ++nlog;
+          if (s >= n) {
+            done = true;
+          } else {
+            base = c.rs[ss * 32];
+            base_regular = regular && (base == 0.f || (fabsf(base) >= 0.0009765625f && fabsf(base) < 262144.f));
+            // slide the text window so that it is anchored at s; prefetch the new tail word
+            if ((s >> 2) != ((s - mblen) >> 2)) {
+              w0 = w1; w1 = w2; w2 = w3;
+              w3 = c.text_w[static_cast<size_t>((s >> 2) + 3) * 32];
+            }
+            cur = window_low();
+            mblen = one_char_len(static_cast<uint32_t>(cur) & 0xFFu);
+            if (mblen > n - s) mblen = n - s;
+            k = s;
+            l = root;
+            has_single = false;
+          }
+        }
+      }
+    }
+    lane_finish(M, B, c, n, nlog, lane, have, defer, sent, bf);  // K4
+    lane_drain(B, sent, have, lane);  // K6 (fused host path only)
+    __syncwarp();
+  }
+}
+
+
 }  // namespace spm_b200
 #endif

@@ -102,5 +102,30 @@ __global__ void __launch_bounds__(kOrderThreads) order_scatter_kernel(const uint
   }
 }
 
+// Samples the batch's bytes for the share of ASCII spaces (the engine picks the unigram lane kernel's instantiation
+// from it, engine.cu pick_fast_words): gridDim.x windows of 4096 bytes spread over [offsets[0], offsets[n]);
+// out[0] += spaces, out[1] += bytes looked at.
+__global__ void __launch_bounds__(256) sample_spaces_kernel(const uint8_t *bytes, const uint64_t *offsets, uint32_t n,
+                                                            unsigned long long *out) {
+  const unsigned long long lo = offsets[0], hi = offsets[n];
+  if (hi <= lo) return;
+  const unsigned long long total = hi - lo;
+  const unsigned long long win = total < 4096ull ? total : 4096ull;
+  const unsigned long long start = gridDim.x > 1 ? lo + (total - win) * blockIdx.x / (gridDim.x - 1) : lo;
+  uint32_t spaces = 0, seen = 0;
+  for (unsigned long long k = threadIdx.x; k < win; k += blockDim.x) {
+    spaces += bytes[start + k] == 0x20u;
+    ++seen;
+  }
+  for (int d = 16; d > 0; d >>= 1) {
+    spaces += __shfl_xor_sync(0xFFFFFFFFu, spaces, d);
+    seen += __shfl_xor_sync(0xFFFFFFFFu, seen, d);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(out, static_cast<unsigned long long>(spaces));
+    atomicAdd(out + 1, static_cast<unsigned long long>(seen));
+  }
+}
+
 }  // namespace spm_b200
 #endif
