@@ -6,15 +6,16 @@
  * simplest thing that is obviously right (a hashed trie, arrays, a binary heap);
  * no attempt is made to be fast.
  *
- * Parity status: PINNED.  tests/test_oracle_vs_reference.py checks this file
+ * Parity status: PINNED.  The CPU tests check this file
  *   (a) against the reference's own known-answer vectors for the path
  *       (src/normalizer_test.cc:37-357, src/unigram_model_test.cc:782-928,
  *        src/bpe_model_test.cc:49-250, src/sentencepiece_processor_test.cc:186-303,
- *        src/util_test.cc:127-226) restated as fixtures in tests/golden/kat_*.json,
+ *        src/util_test.cc:127-226), restated in tests/test_oracle_kat.py,
  *   (b) against outputs of the reference itself: the UNMODIFIED reference compiled
- *       into oracle/_ref (ctypes shim oracle/ref_shim.cc) on seeded corpora, and
- *       the committed golden id dumps under tests/golden/ produced by
- *       tools/make_golden.py with that same compiled reference.
+ *       into oracle/_ref (ctypes shim oracle/ref_shim.cc) on seeded corpora
+ *       (tests/test_oracle_golden.py, test_oracle_nbest.py, test_oracle_lattice.py,
+ *       test_oracle_decode.py), and the committed golden id dumps under tests/golden/
+ *       produced by tools/make_golden.py with that same compiled reference.
  */
 #include "spm_oracle.h"
 

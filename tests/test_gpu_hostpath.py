@@ -103,6 +103,15 @@ def test_large_batch_rejects_decreasing_offsets(corpus_gen):
         eng.encode_packed(buf, bad)
     a, ao = eng.encode_packed(buf, offs)  # the engine is still usable
     assert len(ao) == N + 1 and int(ao[-1]) == len(a)
+    # offsets that point far outside the batch's buffer (the fused path launches before the host has validated them):
+    # the kernels must not touch those sentences, the call fails with the same error, and the context stays healthy
+    wild = offs.copy()
+    wild[2000] = np.uint64(10 ** 12)
+    wild[2001] = np.uint64(10 ** 12 + 5)
+    with pytest.raises(RuntimeError, match="non-decreasing"):
+        eng.encode_packed(buf, wild)
+    a2, ao2 = eng.encode_packed(buf, offs)
+    assert np.array_equal(ao2, ao) and np.array_equal(a2, a)
     eng.close()
 
 
