@@ -18,8 +18,9 @@
 //      slots, unused slots are marked empty.
 //   K4 each lane turns its sentence's log into ids (unk-run merging / byte fallback) as before.
 //
-// Engine-side preconditions as for encode_bpe_lane_kernel.  A word of more than kBpeWordSyms characters defers
-// its sentence to the general kernel.
+// Engine-side preconditions as for encode_bpe_lane_kernel.  A word of more than kBpeWordSyms characters runs the same
+// merge loop with its symbol arrays in HBM scratch (rare; no sentence is deferred for it: the fused host path has no
+// second pass).
 #ifndef SPM_B200_BPE_LANE2_KERNEL_CUH_
 #define SPM_B200_BPE_LANE2_KERNEL_CUH_
 
@@ -31,8 +32,110 @@ constexpr uint32_t kBpeListCap = 128;       // slow words listed per warp before
 constexpr uint32_t kBpeLogEmpty = 0xFFFFFFFFu;
 constexpr uint32_t kBpeLane2WarpBytes = kBpeLaneWarpBytes + kBpeListCap * 8;
 
+// The reference's merge loop on ONE word (bpe_model.cc:110-173 restricted to the word, see the header): the word is
+// `m0` characters starting at byte `p` of the text column `tw`; its symbols end up in the m0 log slots at `lg`
+// (unused slots marked empty).  sym / pn / ps are the symbol arrays, element i at [i * st]: shared memory with
+// st = 32 for words of <= kBpeWordSyms characters, the warp's scratch in HBM with st = 1 for longer ones.
+__device__ __forceinline__ void bpe_merge_word(const KModel &M, const uint32_t *tlink, uint32_t root, const uint32_t *tw,
+                                               uint32_t p, uint32_t m0, uint32_t *lg, uint32_t *sym, uint32_t *pn,
+                                               float *ps, const uint32_t st) {
+  // the first 16 bytes of the word's text in registers (every byte is read several times: character split,
+  // every pair evaluation); longer words read their tail from the slab
+  const uint32_t pw = p >> 2;
+  const uint32_t r0 = tw[static_cast<size_t>(pw) * 32], r1 = tw[static_cast<size_t>(pw + 1) * 32],
+                 r2 = tw[static_cast<size_t>(pw + 2) * 32], r3 = tw[static_cast<size_t>(pw + 3) * 32];
+  auto text_byte = [&](uint32_t k) -> uint32_t {
+    const uint32_t wi = (k >> 2) - pw;
+    uint32_t w;
+    if (wi < 4u) w = (wi & 2u) ? ((wi & 1u) ? r3 : r2) : ((wi & 1u) ? r1 : r0);
+    else w = tw[static_cast<size_t>(k >> 2) * 32];
+    return (w >> ((k & 3u) * 8u)) & 0xFFu;
+  };
+  // walks `len` bytes at text offset `off` from link word `l`; returns the node reached or kBpeDead
+  auto walk = [&](uint32_t l, uint32_t off, uint32_t len, uint32_t *link_out) -> uint32_t {
+    uint32_t v = kBpeDead;
+    for (uint32_t i = 0; i < len; ++i) {
+      const uint32_t ch = text_byte(off + i);
+      v = (l >> kLinkBaseShift) ^ ch;
+      l = __ldg(&tlink[v]);
+      if ((l & kLinkLabelMask) != ch) return kBpeDead;
+    }
+    *link_out = l;
+    return v;
+  };
+  // -- split the word into characters (bpe_model.cc:110-120) and cache their trie nodes --
+  uint32_t m = 0, q = p;
+  for (; m < m0; ++m) {
+    uint32_t l = one_char_len(text_byte(q));
+    uint32_t lk = 0;
+    const uint32_t node = walk(root, q, l, &lk);
+    sym[m * st] = node | (l << 22);
+    pn[m * st] = kBpeDead | ((q - p) << 22);
+    q += l;
+  }
+  // MaybeAddNewSymbolPair (bpe_model.cc:83-107) for the pair (i, i+1)
+  auto eval_pair = [&](uint32_t i) {
+    const uint32_t si = sym[i * st], sj = sym[(i + 1) * st];
+    const uint32_t offj = pn[(i + 1) * st] >> 22;
+    uint32_t res = kBpeDead;
+    float score = 0.f;
+    if ((si & 0x3FFFFFu) != kBpeDead) {
+      uint32_t lk = 0;
+      const uint32_t v = walk(__ldg(&tlink[si & 0x3FFFFFu]), p + offj, sj >> 22, &lk);
+      if (v != kBpeDead && ((lk >> kLinkKindShift) & 3u) != kKindNone) {
+        res = v;
+        score = __uint_as_float(__ldg(M.trie_val + v));
+      }
+    }
+    pn[i * st] = res | (pn[i * st] & 0xFFC00000u);
+    ps[i * st] = score;
+  };
+  for (uint32_t i = 0; i + 1 < m; ++i) eval_pair(i);
+  // -- greedy merges: best score, leftmost on ties (bpe_model.cc:51-57,141-173) --
+  for (;;) {
+    int bi = -1;
+    float best = 0.f;
+    for (uint32_t i = 0; i + 1 < m; ++i) {
+      if ((pn[i * st] & 0x3FFFFFu) != kBpeDead) {
+        const float sc = ps[i * st];
+        if (bi < 0 || sc > best) { best = sc; bi = static_cast<int>(i); }
+      }
+    }
+    if (bi < 0) break;
+    const uint32_t i = static_cast<uint32_t>(bi);
+    const uint32_t nl = (sym[i * st] >> 22) + (sym[(i + 1) * st] >> 22);
+    sym[i * st] = (pn[i * st] & 0x3FFFFFu) | (nl << 22);
+    for (uint32_t jj = i + 1; jj + 1 < m; ++jj) {  // close the gap
+      sym[jj * st] = sym[(jj + 1) * st];
+      pn[jj * st] = pn[(jj + 1) * st];
+      ps[jj * st] = ps[(jj + 1) * st];
+    }
+    --m;
+    if (i > 0) eval_pair(i - 1);
+    if (i + 1 < m) eval_pair(i);
+    else pn[i * st] = kBpeDead | (pn[i * st] & 0xFFC00000u);
+  }
+  // -- the word's symbols go to its slots of the owner's log: PieceToId (model_interface.cc:51-61) --
+  for (uint32_t i = 0; i < m0; ++i) {
+    uint32_t entry = kBpeLogEmpty;
+    if (i < m) {
+      const uint32_t s = sym[i * st];
+      int32_t id = M.unk_id;
+      if ((s & 0x3FFFFFu) != kBpeDead) {
+        const int32_t t = __ldg(M.trie_id + (s & 0x3FFFFFu));
+        if (t >= 0) id = t;
+      }
+      entry = static_cast<uint32_t>(id) | ((s >> 22) << 24);
+    }
+    lg[static_cast<size_t>(i) * 32] = entry;
+  }
+}
+
+// scratch in HBM for the symbol arrays of a long word (one word at a time per warp): sym, pn, ps of cap + 4 entries
+__host__ __device__ inline unsigned long long bpe_long_bytes(uint32_t cap) { return 3ull * (cap + 4u) * 4ull; }
+
 __global__ void __launch_bounds__(768, 1) encode_bpe_lane2_kernel(const KModel M, const KBatch B, uint8_t *slabs,
-                                                                   uint32_t cap) {
+                                                                   uint32_t cap, uint8_t *long_scratch) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint32_t *s_tab = reinterpret_cast<uint32_t *>(smem);
   uint8_t *arrays = smem + kLaneTableBytes;
@@ -42,6 +145,7 @@ __global__ void __launch_bounds__(768, 1) encode_bpe_lane2_kernel(const KModel M
   const uint32_t warp_in_cta = threadIdx.x >> 5;
   const uint32_t warp_global = blockIdx.x * (blockDim.x >> 5) + warp_in_cta;
   LaneCtx c;
+  c.pol = slab_policy(B.slab_l2);
   uint32_t *sym, *pn, *list;
   float *ps;
   uint32_t *text_all, *log_all;  // the warp's slab without the lane offset (phase B reads other lanes' columns)
@@ -56,6 +160,7 @@ __global__ void __launch_bounds__(768, 1) encode_bpe_lane2_kernel(const KModel M
     log_all = reinterpret_cast<uint32_t *>(slab) + static_cast<size_t>(cap / 4 + kLaneTextSlack) * 32;
     c.text_w = text_all + lane;
     c.log = log_all + lane;
+    long_scratch += static_cast<size_t>(warp_global) * bpe_long_bytes(cap);
     c.rs = nullptr;
     c.rb = nullptr;
     c.s_lead = s_tab;
@@ -95,102 +200,24 @@ __global__ void __launch_bounds__(768, 1) encode_bpe_lane2_kernel(const KModel M
     auto drain = [&]() {
       for (uint32_t j0 = 0; j0 < count; j0 += 32) {
         const uint32_t j = j0 + lane;
+        uint32_t owner = 0, p = 0, m0 = 0, slot = 0;
         if (j < count) {
           const uint32_t e0 = list[2 * j], e1 = list[2 * j + 1];
-          const uint32_t owner = e0 & 31u, p = e0 >> 5;       // sentence (lane) and text position of the word
-          const uint32_t m0 = e1 & 63u, slot = e1 >> 6;       // characters, first log slot
-          const uint32_t *tw = text_all + owner;
-          // the first 16 bytes of the word's text in registers (every byte is read several times: character split,
-          // every pair evaluation); longer words read their tail from the slab
-          const uint32_t pw = p >> 2;
-          const uint32_t r0 = tw[static_cast<size_t>(pw) * 32], r1 = tw[static_cast<size_t>(pw + 1) * 32],
-                         r2 = tw[static_cast<size_t>(pw + 2) * 32], r3 = tw[static_cast<size_t>(pw + 3) * 32];
-          auto text_byte = [&](uint32_t k) -> uint32_t {
-            const uint32_t wi = (k >> 2) - pw;
-            uint32_t w;
-            if (wi < 4u) w = (wi & 2u) ? ((wi & 1u) ? r3 : r2) : ((wi & 1u) ? r1 : r0);
-            else w = tw[static_cast<size_t>(k >> 2) * 32];
-            return (w >> ((k & 3u) * 8u)) & 0xFFu;
-          };
-          // walks `len` bytes at text offset `off` from link word `l`; returns the node reached or kBpeDead
-          auto walk = [&](uint32_t l, uint32_t off, uint32_t len, uint32_t *link_out) -> uint32_t {
-            uint32_t v = kBpeDead;
-            for (uint32_t i = 0; i < len; ++i) {
-              const uint32_t ch = text_byte(off + i);
-              v = (l >> kLinkBaseShift) ^ ch;
-              l = __ldg(&tlink[v]);
-              if ((l & kLinkLabelMask) != ch) return kBpeDead;
-            }
-            *link_out = l;
-            return v;
-          };
-          // -- split the word into characters (bpe_model.cc:110-120) and cache their trie nodes --
-          uint32_t m = 0, q = p;
-          for (; m < m0; ++m) {
-            uint32_t l = one_char_len(text_byte(q));
-            uint32_t lk = 0;
-            const uint32_t node = walk(root, q, l, &lk);
-            sym[m * 32] = node | (l << 22);
-            pn[m * 32] = kBpeDead | ((q - p) << 22);
-            q += l;
+          owner = e0 & 31u; p = e0 >> 5;         // sentence (lane) and text position of the word
+          m0 = e1 & 0xFFFu; slot = e1 >> 12;     // characters, first log slot
+          if (m0 <= kBpeWordSyms)
+            bpe_merge_word(M, tlink, root, text_all + owner, p, m0, log_all + owner + static_cast<size_t>(slot) * 32, sym, pn,
+                           ps, 32u);
+        }
+        // words of more symbols than the shared arrays hold (URLs, long numbers: ~0.4 per 1000 sentences of the bench
+        // corpus): one at a time, on the lane that drew the word, with the symbol arrays in the warp's HBM scratch
+        for (uint32_t todo = __ballot_sync(0xFFFFFFFFu, m0 > kBpeWordSyms); todo; todo &= todo - 1u) {
+          if (lane == static_cast<uint32_t>(__ffs(todo)) - 1u) {
+            uint32_t *g = reinterpret_cast<uint32_t *>(long_scratch);
+            bpe_merge_word(M, tlink, root, text_all + owner, p, m0, log_all + owner + static_cast<size_t>(slot) * 32, g,
+                           g + (cap + 4u), reinterpret_cast<float *>(g + 2u * (cap + 4u)), 1u);
           }
-          // MaybeAddNewSymbolPair (bpe_model.cc:83-107) for the pair (i, i+1)
-          auto eval_pair = [&](uint32_t i) {
-            const uint32_t si = sym[i * 32], sj = sym[(i + 1) * 32];
-            const uint32_t offj = pn[(i + 1) * 32] >> 22;
-            uint32_t res = kBpeDead;
-            float score = 0.f;
-            if ((si & 0x3FFFFFu) != kBpeDead) {
-              uint32_t lk = 0;
-              const uint32_t v = walk(__ldg(&tlink[si & 0x3FFFFFu]), p + offj, sj >> 22, &lk);
-              if (v != kBpeDead && ((lk >> kLinkKindShift) & 3u) != kKindNone) {
-                res = v;
-                score = __uint_as_float(__ldg(M.trie_val + v));
-              }
-            }
-            pn[i * 32] = res | (pn[i * 32] & 0xFFC00000u);
-            ps[i * 32] = score;
-          };
-          for (uint32_t i = 0; i + 1 < m; ++i) eval_pair(i);
-          // -- greedy merges: best score, leftmost on ties (bpe_model.cc:51-57,141-173) --
-          for (;;) {
-            int bi = -1;
-            float best = 0.f;
-            for (uint32_t i = 0; i + 1 < m; ++i) {
-              if ((pn[i * 32] & 0x3FFFFFu) != kBpeDead) {
-                const float sc = ps[i * 32];
-                if (bi < 0 || sc > best) { best = sc; bi = static_cast<int>(i); }
-              }
-            }
-            if (bi < 0) break;
-            const uint32_t i = static_cast<uint32_t>(bi);
-            const uint32_t nl = (sym[i * 32] >> 22) + (sym[(i + 1) * 32] >> 22);
-            sym[i * 32] = (pn[i * 32] & 0x3FFFFFu) | (nl << 22);
-            for (uint32_t jj = i + 1; jj + 1 < m; ++jj) {  // close the gap
-              sym[jj * 32] = sym[(jj + 1) * 32];
-              pn[jj * 32] = pn[(jj + 1) * 32];
-              ps[jj * 32] = ps[(jj + 1) * 32];
-            }
-            --m;
-            if (i > 0) eval_pair(i - 1);
-            if (i + 1 < m) eval_pair(i);
-            else pn[i * 32] = kBpeDead | (pn[i * 32] & 0xFFC00000u);
-          }
-          // -- the word's symbols go to its slots of the owner's log: PieceToId (model_interface.cc:51-61) --
-          uint32_t *lg = log_all + owner + static_cast<size_t>(slot) * 32;
-          for (uint32_t i = 0; i < m0; ++i) {
-            uint32_t entry = kBpeLogEmpty;
-            if (i < m) {
-              const uint32_t s = sym[i * 32];
-              int32_t id = M.unk_id;
-              if ((s & 0x3FFFFFu) != kBpeDead) {
-                const int32_t t = __ldg(M.trie_id + (s & 0x3FFFFFu));
-                if (t >= 0) id = t;
-              }
-              entry = static_cast<uint32_t>(id) | ((s >> 22) << 24);
-            }
-            lg[static_cast<size_t>(i) * 32] = entry;
-          }
+          __syncwarp();
         }
       }
       count = 0;
@@ -224,8 +251,6 @@ __global__ void __launch_bounds__(768, 1) encode_bpe_lane2_kernel(const KModel M
           if (fast_id != 0xFFFFFFFFu) {
             c.log[static_cast<size_t>(nlog) * 32] = fast_id | ((k - wp) << 24);
             ++nlog;
-          } else if (m > kBpeWordSyms) {
-            defer = true;  // a word of too many symbols: the general kernel takes the sentence
           } else {
             slow = true;
             slow_p = wp; slow_m = m; slow_slot = nlog;
@@ -254,7 +279,7 @@ __global__ void __launch_bounds__(768, 1) encode_bpe_lane2_kernel(const KModel M
         if (slow) {
           const uint32_t idx = count + __popc(m_slow & ((1u << lane) - 1u));
           list[2 * idx] = lane | (slow_p << 5);
-          list[2 * idx + 1] = slow_m | (slow_slot << 6);
+          list[2 * idx + 1] = slow_m | (slow_slot << 12);
         }
         count += __popc(m_slow);
         __syncwarp();

@@ -39,6 +39,7 @@ __global__ void __launch_bounds__(768, 1) encode_bpe_lane_kernel(const KModel M,
   const uint32_t warp_in_cta = threadIdx.x >> 5;
   const uint32_t warp_global = blockIdx.x * (blockDim.x >> 5) + warp_in_cta;
   LaneCtx c;
+  c.pol = slab_policy(B.slab_l2);
   uint32_t *sym, *pn;
   float *ps;
   {

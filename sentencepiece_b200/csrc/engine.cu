@@ -154,11 +154,12 @@ struct spm_engine {
   int G = 1;  // 1: lane kernel (sentence per lane); 32: warp kernel; 4/8/16: tile kernel; 64: tile kernel, 32 lanes
   int threads = 1024;
   uint32_t ncap = 256;
+  uint32_t slab_l2 = 0;    // SPM_B200_SLAB_L2: L2 eviction priority of the slab accesses (KBatch::slab_l2)
   uint32_t lane_cap = 512;  // normalized-byte capacity per sentence of the lane kernel's slabs
   int ctas_per_sm = 1;
 
   // per-call buffers (grow only)
-  DevBuf<uint8_t> d_bytes, d_tmp_norm, d_norm, d_long_scratch, d_lane_slabs;
+  DevBuf<uint8_t> d_bytes, d_tmp_norm, d_norm, d_long_scratch, d_lane_slabs, d_bpe_long;
   DevBuf<uint64_t> d_offsets;
   DevBuf<int32_t> d_tmp_ids, d_ids;
   DevBuf<uint32_t> d_tmp_tok_end, d_tok_end, d_tmp_n2o, d_n2o, d_sent_count, d_norm_len, d_deferred, d_deferred2, d_long_list, d_ctrl32;
@@ -845,6 +846,7 @@ int spm_engine::run_device(const uint8_t *d_bytes_base, const uint64_t *d_offs, 
     geom.smem_bytes = lg.smem;
     const size_t warps_total = static_cast<size_t>(sm_count) * ctas_per_sm * geom.tiles;
     CUDA_TRY(d_lane_slabs.ensure(warps_total * lane_slab_bytes(lane_cap) + 256));
+    if (bpe) CUDA_TRY(d_bpe_long.ensure(warps_total * bpe_long_bytes(lane_cap)));
   }
   if (geom.smem_bytes > smem_optin) { set_error("shared-memory geometry does not fit; lower smem_norm_cap"); return SPM_ERR_ARG; }
   KModel M = km;
@@ -879,6 +881,7 @@ int spm_engine::run_device(const uint8_t *d_bytes_base, const uint64_t *d_offs, 
     CUDA_TRY(cudaMemsetAsync(d_ctrl32.p, 0, 16 * sizeof(uint32_t), st));
     CUDA_TRY(cudaMemsetAsync(d_ctrl64.p, 0, 4 * sizeof(unsigned long long), st));
     KBatch B{};
+    B.slab_l2 = slab_l2;
     B.bytes = d_bytes_base;
     B.offsets = d_offs;
     B.n = n32;
@@ -917,7 +920,7 @@ int spm_engine::run_device(const uint8_t *d_bytes_base, const uint64_t *d_offs, 
       B.piece_shift = cur_piece_shift;
     }
     if (bpe_lane_path && lg.version == 2) {
-      encode_bpe_lane2_kernel<<<grid, lg.threads, geom.smem_bytes, st>>>(M, B, d_lane_slabs.p, lane_cap);
+      encode_bpe_lane2_kernel<<<grid, lg.threads, geom.smem_bytes, st>>>(M, B, d_lane_slabs.p, lane_cap, d_bpe_long.p);
     } else if (bpe_lane_path) {
       encode_bpe_lane_kernel<<<grid, lg.threads, geom.smem_bytes, st>>>(M, B, d_lane_slabs.p, lane_cap);
     } else if (bpe) {
@@ -1408,6 +1411,7 @@ int spm_engine::encode_host_fused(const char *bytes, const uint64_t *offsets, si
   const uint32_t smem = lg.smem;
   const int grid = sm_count * ctas_per_sm;
   CUDA_TRY(d_lane_slabs.ensure(static_cast<size_t>(grid) * (lane_threads / 32) * lane_slab_bytes(lane_cap) + 256));
+  if (bpe) CUDA_TRY(d_bpe_long.ensure(static_cast<size_t>(grid) * (lane_threads / 32) * bpe_long_bytes(lane_cap)));
   // ---- queue the whole input ----
   CUDA_TRY(cudaMemsetAsync(d_ready.p, 0, sizeof(uint32_t), s_h2d));
   CUDA_TRY(cudaMemcpyAsync(s_offsets.p, offsets, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s_h2d));
@@ -1444,6 +1448,7 @@ int spm_engine::encode_host_fused(const char *bytes, const uint64_t *offsets, si
   KModel M = km;
   M.hot_link = M.hot_val = 0;
   KBatch B{};
+  B.slab_l2 = slab_l2;
   B.bytes = s_bytes.p - offsets[0];
   B.offsets = s_offsets.p;
   B.n = n32;
@@ -1488,7 +1493,7 @@ int spm_engine::encode_host_fused(const char *bytes, const uint64_t *offsets, si
   if (const char *v = getenv("SPM_B200_SORT_SHIFT")) sort_shift = std::min<uint32_t>(kPieceShift, std::max<uint32_t>(kSegShift, atoi(v)));
   { const int rc = build_order(s_offsets.p, n, st, &B.order, 1u << sort_shift); if (rc) return rc; }
   if (!B.order) { set_error("fused path needs the segment order"); return SPM_ERR_ARG; }
-  if (bpe && lg.version == 2) encode_bpe_lane2_kernel<<<grid, lane_threads, smem, st>>>(M, B, d_lane_slabs.p, lane_cap);
+  if (bpe && lg.version == 2) encode_bpe_lane2_kernel<<<grid, lane_threads, smem, st>>>(M, B, d_lane_slabs.p, lane_cap, d_bpe_long.p);
   else if (bpe) encode_bpe_lane_kernel<<<grid, lane_threads, smem, st>>>(M, B, d_lane_slabs.p, lane_cap);
   else if (lg.version == 2) encode_unigram_lane_kernel<<<grid, lane_threads, smem, st>>>(M, B, d_lane_slabs.p, lane_cap, lg.R);
   else encode_unigram_lane_plain_kernel<<<grid, lane_threads, smem, st>>>(M, B, d_lane_slabs.p, lane_cap, lg.R);
@@ -1833,6 +1838,7 @@ int spm_engine::run_nbest(const char *bytes, const uint64_t *offsets, size_t n, 
     CUDA_TRY(cudaMemsetAsync(d_ctrl32.p, 0, 16 * sizeof(uint32_t), st));
     CUDA_TRY(cudaMemsetAsync(d_ctrl64.p, 0, 4 * sizeof(unsigned long long), st));
     KBatch B{};
+    B.slab_l2 = slab_l2;
     B.bytes = d_bytes.p - base;
     B.offsets = d_offsets.p;
     B.n = static_cast<uint32_t>(n);
@@ -1937,6 +1943,7 @@ int spm_engine::run_lattice(const char *bytes, const uint64_t *offsets, size_t n
       CUDA_TRY(cudaMemsetAsync(d_ctrl32.p, 0, 16 * sizeof(uint32_t), st));
       CUDA_TRY(cudaMemsetAsync(d_ctrl64.p, 0, 4 * sizeof(unsigned long long), st));
       KBatch B{};
+      B.slab_l2 = slab_l2;
       B.bytes = d_bytes.p - base;
       B.offsets = d_offsets.p;
       B.n = static_cast<uint32_t>(m);
@@ -2099,6 +2106,8 @@ static int create_common(spm_engine *e, int device, spm_engine **out) {
   if (const char *v = getenv("SPM_B200_FUSED")) e->fused_host_path = atoi(v) != 0;
   if (const char *v = getenv("SPM_B200_FASTWORDS")) e->force_fast_words = atoi(v) != 0 ? 1 : 0;
   if (const char *v = getenv("SPM_B200_KSTATS")) e->kstats = atoi(v) != 0;
+  if (const char *v = getenv("SPM_B200_SLAB_L2")) e->slab_l2 = static_cast<uint32_t>(atoi(v));
+  if (const char *v = getenv("SPM_B200_LANE_CAP")) e->lane_cap = std::min(1020, std::max(64, atoi(v))) & ~3;
   if (const char *v = getenv("SPM_B200_BPE_LANE_V")) e->bpe_lane_version = atoi(v);
   e->smem_optin = prop.sharedMemPerBlockOptin;
   if (cudaSetDevice(device) != cudaSuccess) return fail(SPM_ERR_CUDA, "cudaSetDevice failed");
@@ -2165,7 +2174,7 @@ void spm_engine_destroy(spm_engine *e) {
   e->d_ctrl32.release(); e->d_sent_start.release(); e->d_norm_start.release(); e->d_id_offsets.release();
   e->d_norm_offsets.release(); e->d_n2o_offsets.release(); e->d_block_sums.release(); e->d_ctrl64.release();
   e->d_long_off.release();
-  e->d_lane_slabs.release();
+  e->d_lane_slabs.release(); e->d_bpe_long.release();
   e->d_node2.release();
   e->d_lat_scratch.release(); e->d_lat_nodes.release(); e->d_lat_pos.release(); e->d_lat_node_start.release();
   e->d_lat_pos_start.release(); e->d_lat_nchars.release(); e->d_lat_entropy.release(); e->h_lat_nodes.release();

@@ -108,7 +108,28 @@ struct LaneCtx {
   const int32_t *s_solo;
   const uint32_t *s_plain;  // bit b: ASCII byte b is copied verbatim (no rule starts with it, not a space)
   const uint32_t *s_plainsp;  // bit b: ASCII byte b followed by an ASCII byte is always its own chunk (space included)
+  unsigned long long pol;     // L2 cache policy of the slab accesses (slab_policy())
 };
+
+// The per-lane slabs (normalized text, back-pointer log) are written and read back within one group: ~12 KB per
+// resident warp, ~40 MB per GPU, which fits L2 -- but only stays there if the batch's streamed input and ids do not
+// push it out.  Every slab access carries an L2 eviction-priority hint (evict_last); the once-read input and the
+// once-written ids use the streaming forms (__ldcs / __stcs).
+__device__ __forceinline__ unsigned long long slab_policy(uint32_t mode) {
+  unsigned long long pol;
+  if (mode == 1u) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  else if (mode == 2u) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint32_t slab_ld(const uint32_t *p, unsigned long long pol) {
+  uint32_t v;
+  asm volatile("ld.global.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol) : "memory");
+  return v;
+}
+__device__ __forceinline__ void slab_st(uint32_t *p, uint32_t v, unsigned long long pol) {
+  asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" :: "l"(p), "r"(v), "l"(pol) : "memory");
+}
 
 // Sequential byte stream over a lane's input: 16-byte aligned chunks (next chunk prefetched)
 // feed a 64-bit shift register that always exposes the next >= 4 bytes.  The aligned chunks
@@ -177,7 +198,7 @@ __device__ __forceinline__ uint32_t lane_normalize(const KModel &M, const uint8_
   auto put = [&](uint32_t ch) {
     acc |= ch << ((out & 3u) * 8u);
     if ((out & 3u) == 3u) {
-      if (out < cap) c.text_w[static_cast<size_t>(out >> 2) * 32] = acc; else overflow = true;
+      if (out < cap) slab_st(c.text_w + static_cast<size_t>(out >> 2) * 32, acc, c.pol); else overflow = true;
       acc = 0;
     }
     ++out;
@@ -223,8 +244,8 @@ __device__ __forceinline__ uint32_t lane_normalize(const KModel &M, const uint8_
         const uint32_t nw = ((out & 3u) + clen) >> 2;  // full words completed: 0..2
         if (out <= cap) {
           uint32_t *wp = c.text_w + static_cast<size_t>(out >> 2) * 32;
-          if (nw >= 1) wp[0] = static_cast<uint32_t>(lo);
-          if (nw >= 2) wp[32] = static_cast<uint32_t>(lo >> 32);
+          if (nw >= 1) slab_st(wp + 0, static_cast<uint32_t>(lo), c.pol);
+          if (nw >= 2) slab_st(wp + 32, static_cast<uint32_t>(lo >> 32), c.pol);
         }
         acc = nw == 0 ? static_cast<uint32_t>(lo) : (nw == 1 ? static_cast<uint32_t>(lo >> 32) : hi);
         out += clen;
@@ -341,10 +362,10 @@ __device__ __forceinline__ uint32_t lane_normalize(const KModel &M, const uint8_
   if (!started) return 0;  // all chars are whitespace (:97-100)
   if (overflow || out > cap) return 0xFFFFFFFFu;
   // flush the partial word, then strip trailing spaces on the escaped output (:166-176)
-  c.text_w[static_cast<size_t>(out >> 2) * 32] = acc;
+  slab_st(c.text_w + static_cast<size_t>(out >> 2) * 32, acc, c.pol);
   if (rm) {
     auto byte_at = [&](uint32_t k) -> uint32_t {
-      return (c.text_w[static_cast<size_t>(k >> 2) * 32] >> ((k & 3u) * 8u)) & 0xFFu;
+      return (slab_ld(c.text_w + static_cast<size_t>(k >> 2) * 32, c.pol) >> ((k & 3u) * 8u)) & 0xFFu;
     };
     if (esc) {
       while (out >= 3 && byte_at(out - 3) == 0xE2 && byte_at(out - 2) == 0x96 && byte_at(out - 1) == 0x81) out -= 3;
@@ -354,9 +375,9 @@ __device__ __forceinline__ uint32_t lane_normalize(const KModel &M, const uint8_
   }
   if (suffix && addp) {  // :179
     if (out + 3 > cap) return 0xFFFFFFFFu;
-    acc = (out & 3u) ? (c.text_w[static_cast<size_t>(out >> 2) * 32] & ((1u << ((out & 3u) * 8u)) - 1u)) : 0u;
+    acc = (out & 3u) ? (slab_ld(c.text_w + static_cast<size_t>(out >> 2) * 32, c.pol) & ((1u << ((out & 3u) * 8u)) - 1u)) : 0u;
     put_ws();
-    c.text_w[static_cast<size_t>(out >> 2) * 32] = acc;
+    slab_st(c.text_w + static_cast<size_t>(out >> 2) * 32, acc, c.pol);
   }
   return out;
 }
@@ -380,7 +401,7 @@ __device__ __forceinline__ void lane_finish(const KModel &M, const KBatch &B, co
 #pragma unroll
       for (int j = 0; j < 4; ++j) {  // four independent, coalesced loads per trip
         const uint32_t t = tb - 1 - j;
-        ev[j] = t < nlog ? c.log[static_cast<size_t>(t) * 32] : 0u;
+        ev[j] = t < nlog ? slab_ld(c.log + static_cast<size_t>(t) * 32, c.pol) : 0u;
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -430,7 +451,7 @@ __device__ __forceinline__ void lane_finish(const KModel &M, const KBatch &B, co
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const uint32_t t = tb - 1 - j;
-        ev[j] = t < nlog ? c.log[static_cast<size_t>(t) * 32] : 0u;
+        ev[j] = t < nlog ? slab_ld(c.log + static_cast<size_t>(t) * 32, c.pol) : 0u;
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -445,7 +466,7 @@ __device__ __forceinline__ void lane_finish(const KModel &M, const KBatch &B, co
             if (bf) {
               for (uint32_t i = 0; i < plen; ++i) {
                 const uint32_t kk = want - 1 - i;
-                const uint32_t ch = (c.text_w[static_cast<size_t>(kk >> 2) * 32] >> ((kk & 3u) * 8u)) & 0xFFu;
+                const uint32_t ch = (slab_ld(c.text_w + static_cast<size_t>(kk >> 2) * 32, c.pol) >> ((kk & 3u) * 8u)) & 0xFFu;
                 __stcs(B.tmp_ids + pos + (--w), __ldg(M.byte_to_id + ch));
               }
             } else if (!prev_unk) {
@@ -489,6 +510,7 @@ __global__ void __launch_bounds__(1024, 1) encode_unigram_lane_kernel(const KMod
   const uint32_t warp_in_cta = threadIdx.x >> 5;
   const uint32_t warp_global = blockIdx.x * (blockDim.x >> 5) + warp_in_cta;
   LaneCtx c;
+  c.pol = slab_policy(B.slab_l2);
   uint16_t *rp;  // ring position tags: a slot belongs to position p iff rp == p (no clearing, skipped positions
                  // of whole words leave stale slots behind that simply fail the test)
   {
@@ -562,7 +584,7 @@ __global__ void __launch_bounds__(1024, 1) encode_unigram_lane_kernel(const KMod
     if (!done) {
       for (uint32_t r = 0; r < R; ++r) rp[r * 32] = 0xFFFFu;  // no slot belongs to a position of this sentence
       c.rs[0] = 0.f;
-      w0 = c.text_w[0]; w1 = c.text_w[32]; w2 = c.text_w[64]; w3 = c.text_w[96];
+      w0 = slab_ld(c.text_w + 0, c.pol); w1 = slab_ld(c.text_w + 32, c.pol); w2 = slab_ld(c.text_w + 64, c.pol); w3 = slab_ld(c.text_w + 96, c.pol);
       mblen = one_char_len(w0 & 0xFFu);
       if (mblen > n) mblen = n;
       cur = window_low();
@@ -579,7 +601,7 @@ __global__ void __launch_bounds__(1024, 1) encode_unigram_lane_kernel(const KMod
           const uint32_t d = k - s;
           uint32_t ch;
           if (d >= 13u) {  // beyond the register window: long piece, rare
-            ch = (c.text_w[static_cast<size_t>(k >> 2) * 32] >> ((k & 3u) * 8u)) & 0xFFu;
+            ch = (slab_ld(c.text_w + static_cast<size_t>(k >> 2) * 32, c.pol) >> ((k & 3u) * 8u)) & 0xFFu;
           } else {
             if (d == 8u) cur = window_high();
             ch = static_cast<uint32_t>(cur) & 0xFFu;
@@ -630,7 +652,7 @@ __global__ void __launch_bounds__(1024, 1) encode_unigram_lane_kernel(const KMod
             if (k < n) {
               uint32_t nb;
               const uint32_t d2 = k - s;
-              if (d2 >= 13u) nb = (c.text_w[static_cast<size_t>(k >> 2) * 32] >> ((k & 3u) * 8u)) & 0xFFu;
+              if (d2 >= 13u) nb = (slab_ld(c.text_w + static_cast<size_t>(k >> 2) * 32, c.pol) >> ((k & 3u) * 8u)) & 0xFFu;
               else nb = d2 == 8u ? static_cast<uint32_t>(window_high()) & 0xFFu : static_cast<uint32_t>(cur) & 0xFFu;
               end_walk = !((nd.y >> (nb & 31u)) & 1u);
             }
@@ -653,7 +675,7 @@ __global__ void __launch_bounds__(1024, 1) encode_unigram_lane_kernel(const KMod
               } else {
                 b3 = 0;
                 for (uint32_t i = 0; i < 3u; ++i)
-                  b3 |= ((c.text_w[static_cast<size_t>((k + i) >> 2) * 32] >> (((k + i) & 3u) * 8u)) & 0xFFu) << (8u * i);
+                  b3 |= ((slab_ld(c.text_w + static_cast<size_t>((k + i) >> 2) * 32, c.pol) >> (((k + i) & 3u) * 8u)) & 0xFFu) << (8u * i);
               }
               wend = b3 == kWsWord;
             }
@@ -684,7 +706,7 @@ __global__ void __launch_bounds__(1024, 1) encode_unigram_lane_kernel(const KMod
           }
           if (ss >= r_wrap) ss -= r_wrap;
           // position s is final: append (plen | previous char length or whole-word step | unit) to the log
-          c.log[static_cast<size_t>(nlog) * 32] = c.rb[ss] | steplog;
+          slab_st(c.log + static_cast<size_t>(nlog) * 32, c.rb[ss] | steplog, c.pol);
           ++nlog;
           if (s >= n) {
             done = true;
@@ -695,14 +717,14 @@ __global__ void __launch_bounds__(1024, 1) encode_unigram_lane_kernel(const KMod
             const uint32_t jw = (s >> 2) - (s_old >> 2);
             if (jw == 1u) {
               w0 = w1; w1 = w2; w2 = w3;
-              w3 = c.text_w[static_cast<size_t>((s >> 2) + 3) * 32];
+              w3 = slab_ld(c.text_w + static_cast<size_t>((s >> 2) + 3) * 32, c.pol);
             } else if (jw == 2u) {
               w0 = w2; w1 = w3;
-              w2 = c.text_w[static_cast<size_t>((s >> 2) + 2) * 32];
-              w3 = c.text_w[static_cast<size_t>((s >> 2) + 3) * 32];
+              w2 = slab_ld(c.text_w + static_cast<size_t>((s >> 2) + 2) * 32, c.pol);
+              w3 = slab_ld(c.text_w + static_cast<size_t>((s >> 2) + 3) * 32, c.pol);
             } else if (jw != 0u) {
               const uint32_t *tw = c.text_w + static_cast<size_t>(s >> 2) * 32;
-              w0 = tw[0]; w1 = tw[32]; w2 = tw[64]; w3 = tw[96];
+              w0 = slab_ld(tw + 0, c.pol); w1 = slab_ld(tw + 32, c.pol); w2 = slab_ld(tw + 64, c.pol); w3 = slab_ld(tw + 96, c.pol);
             }
             cur = window_low();
             wstart = (static_cast<uint32_t>(cur) & 0xFFFFFFu) == kWsWord;
@@ -751,6 +773,7 @@ __global__ void __launch_bounds__(1024, 1) encode_unigram_lane_plain_kernel(cons
   const uint32_t warp_in_cta = threadIdx.x >> 5;
   const uint32_t warp_global = blockIdx.x * (blockDim.x >> 5) + warp_in_cta;
   LaneCtx c;
+  c.pol = slab_policy(B.slab_l2);
   {
     uint8_t *ring = rings + static_cast<size_t>(warp_in_cta) * (R * 32 * 8);
     c.rs = reinterpret_cast<float *>(ring) + lane;
@@ -818,7 +841,7 @@ __global__ void __launch_bounds__(1024, 1) encode_unigram_lane_plain_kernel(cons
     if (!done) {
       for (uint32_t r = 0; r < R; ++r) c.rb[r * 32] = 0u;  // all positions unset
       c.rs[0] = 0.f;
-      w0 = c.text_w[0]; w1 = c.text_w[32]; w2 = c.text_w[64]; w3 = c.text_w[96];
+      w0 = slab_ld(c.text_w + 0, c.pol); w1 = slab_ld(c.text_w + 32, c.pol); w2 = slab_ld(c.text_w + 64, c.pol); w3 = slab_ld(c.text_w + 96, c.pol);
       mblen = one_char_len(w0 & 0xFFu);
       if (mblen > n) mblen = n;
       cur = window_low();
@@ -830,7 +853,7 @@ __global__ void __launch_bounds__(1024, 1) encode_unigram_lane_plain_kernel(cons
           const uint32_t d = k - s;
           uint32_t ch;
           if (d >= 13u) {  // beyond the register window: long piece, rare
-            ch = (c.text_w[static_cast<size_t>(k >> 2) * 32] >> ((k & 3u) * 8u)) & 0xFFu;
+            ch = (slab_ld(c.text_w + static_cast<size_t>(k >> 2) * 32, c.pol) >> ((k & 3u) * 8u)) & 0xFFu;
           } else {
             if (d == 8u) cur = window_high();
             ch = static_cast<uint32_t>(cur) & 0xFFu;
@@ -880,7 +903,7 @@ __global__ void __launch_bounds__(1024, 1) encode_unigram_lane_plain_kernel(cons
             if (k < n) {
               uint32_t nb;
               const uint32_t d2 = k - s;
-              if (d2 >= 13u) nb = (c.text_w[static_cast<size_t>(k >> 2) * 32] >> ((k & 3u) * 8u)) & 0xFFu;
+              if (d2 >= 13u) nb = (slab_ld(c.text_w + static_cast<size_t>(k >> 2) * 32, c.pol) >> ((k & 3u) * 8u)) & 0xFFu;
               else nb = d2 == 8u ? static_cast<uint32_t>(window_high()) & 0xFFu : static_cast<uint32_t>(cur) & 0xFFu;
               end_walk = !((nd.y >> (nb & 31u)) & 1u);
             }
@@ -903,7 +926,7 @@ __global__ void __launch_bounds__(1024, 1) encode_unigram_lane_plain_kernel(cons
           s += mblen;
           ss = sl;
           // position s is final: append (plen | previous char length | unit) to the log
-          c.log[static_cast<size_t>(nlog) * 32] = c.rb[ss * 32] | ((mblen - 1u) << 22);
+          slab_st(c.log + static_cast<size_t>(nlog) * 32, c.rb[ss * 32] | ((mblen - 1u) << 22), c.pol);
           ++nlog;
           if (s >= n) {
             done = true;
@@ -913,7 +936,7 @@ __global__ void __launch_bounds__(1024, 1) encode_unigram_lane_plain_kernel(cons
             // slide the text window so that it is anchored at s; prefetch the new tail word
             if ((s >> 2) != ((s - mblen) >> 2)) {
               w0 = w1; w1 = w2; w2 = w3;
-              w3 = c.text_w[static_cast<size_t>((s >> 2) + 3) * 32];
+              w3 = slab_ld(c.text_w + static_cast<size_t>((s >> 2) + 3) * 32, c.pol);
             }
             cur = window_low();
             mblen = one_char_len(static_cast<uint32_t>(cur) & 0xFFu);

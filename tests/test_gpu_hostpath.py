@@ -94,6 +94,41 @@ def test_fused_falls_back_on_long_sentences(corpus_gen):
     ref.close()
 
 
+def test_bpe_long_words_stay_in_the_lane_kernel(corpus_gen):
+    """words of more symbols than the lane kernel's shared arrays hold (URLs, digit runs, unspaced CJK) are merged in
+    the same kernel with HBM scratch: nothing is deferred, so the fused path completes, and the ids are exact."""
+    rng = np.random.default_rng(11)
+    buf, offs = corpus_gen.fill("en", 7003, N)
+    extra = [b"see https://example.org/a/very/long/path/with-many-segments_and_underscores?query=1234567890&k=v#frag now",
+             b"1234567890" * 30,
+             ("\u6771\u4eac\u90fd\u5343\u4ee3\u7530\u533a" * 12).encode("utf-8"),
+             b"a" * 25, b"ab" * 13 + b" " + b"z" * 24, b"x" * 500,
+             ("caf\u00e9" * 40).encode("utf-8") + b" tail"]
+    rb, ro = _ragged(buf, offs, rng, extra * 3)
+    eng = _engine("bpe32k")
+    a, ao = eng.encode_packed(rb, ro)
+    assert eng.info().last_deferred == 0
+    ref = _engine("bpe32k", SPM_B200_FUSED=0, SPM_B200_SORT=0, SPM_B200_BPE_LANE_V=1)
+    b, bo = ref.encode_packed(rb, ro)
+    assert np.array_equal(ao, bo) and np.array_equal(a, b)
+    om = oracle_py.OracleModel(model_bytes("bpe32k"))
+    rraw = rb.tobytes()
+    lens = np.diff(ro)
+    raws = [rraw[int(ro[i]):int(ro[i + 1])] for i in range(len(lens))]
+    check = [i for i, r in enumerate(raws) if r in extra] + list(range(0, len(lens), 9001))
+    assert len(check) >= len(extra) * 3
+    for i in check:
+        assert a[int(ao[i]):int(ao[i + 1])].tolist() == om.encode(raws[i])[0].tolist(), i
+    # the small-batch (device) path takes the same kernel
+    sb, so = _ragged(*corpus_gen.fill("en", 7004, 3000), rng, extra)
+    c, co = eng.encode_packed(sb, so)
+    assert eng.info().last_deferred == 0
+    oc, oco = om.encode_batch(sb, so)
+    assert np.array_equal(co, oco) and np.array_equal(c, oc)
+    eng.close()
+    ref.close()
+
+
 def test_large_batch_rejects_decreasing_offsets(corpus_gen):
     buf, offs = corpus_gen.fill("en", 7003, N)
     bad = offs.copy()

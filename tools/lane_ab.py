@@ -3,7 +3,8 @@
 usage: python tools/lane_ab.py [model:kind ...] [--n N] [--variants "FW=0;FW=1;BV=1;BV=2,T=704"]
 Each variant is a ';'-separated item of ','-separated KEY=VALUE knobs:
   FW whole-word shortcut (SPM_B200_FASTWORDS), S length ordering (SPM_B200_SORT),
-  T threads per CTA, BV BPE lane kernel version (SPM_B200_BPE_LANE_V).
+  T threads per CTA, BV BPE lane kernel version (SPM_B200_BPE_LANE_V), L2 eviction priority of the slab
+  accesses (SPM_B200_SLAB_L2: 0 normal, 1 evict_last, 2 evict_first), CAP slab capacity per lane (SPM_B200_LANE_CAP).
 """
 import argparse
 import os
@@ -18,7 +19,7 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 import corpus  # noqa: E402
 from sentencepiece_b200 import Engine  # noqa: E402
 
-ENV = {"FW": "SPM_B200_FASTWORDS",
+ENV = {"FW": "SPM_B200_FASTWORDS", "L2": "SPM_B200_SLAB_L2", "CAP": "SPM_B200_LANE_CAP",
        "BV": "SPM_B200_BPE_LANE_V", "S": "SPM_B200_SORT"}
 
 ap = argparse.ArgumentParser()
