@@ -80,6 +80,13 @@ void spm_engine_destroy(spm_engine *e);
  * Call with the full types array after either. */
 int spm_engine_set_types(spm_engine *e, const uint8_t *types);
 
+/* Empties the engine's internal memo tables (today: the BPE word cache, which
+ * remembers the ids of words that were merged before; results never depend on
+ * it).  No counterpart in the reference -- bpe::Model has no state across
+ * calls (src/bpe_model.cc:38-203).  For measurements that must not profit
+ * from earlier batches; spm_engine_set_types empties the tables as well. */
+int spm_engine_cache_reset(spm_engine *e);
+
 /* Text of the last failure on this engine (or of the last failed create when
  * e == NULL).  Never NULL. */
 const char *spm_last_error(const spm_engine *e);

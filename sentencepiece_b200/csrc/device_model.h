@@ -64,6 +64,10 @@ struct KModel {
   // [trie_units] BPE lane2 kernel: vocab id of the piece at this unit when a word that is exactly the piece encodes
   // to that single id (its merge sequence reproduces it), else 0xFFFFFFFF
   const uint32_t *word_fast;
+  // BPE lane2 kernel: word cache in HBM (bpe_lane2_kernel.cuh, "word cache"): bpe_cache_mask + 1 entries of 64 bytes,
+  // filled by the kernels themselves; mask 0 = no cache
+  uint4 *bpe_cache;
+  uint32_t bpe_cache_mask;
   int32_t unk_id;
   float unk_score;  // min_score_ - kUnkPenalty, unigram_model.cc:955
   float max_score;  // unigram_model.cc:658-663 (FLT_MIN quirk)
@@ -99,6 +103,7 @@ struct KBatch {
   uint32_t *seg_copied;               // [segments]
   uint32_t *drained_upto;
   unsigned long long *host_progress;
+  uint32_t slab_discard;              // lane kernels: discard.L2 the used slab rows at the end of a group (lane_kernel.cuh)
   uint32_t slab_l2;                   // L2 eviction priority of the lane kernels' slab accesses: 0 normal, 1 evict_last, 2 evict_first
   unsigned long long *kstats;         // [4] cycles (lane 0 of each warp): input wait, compaction, look-back wait, groups; or null
   // outputs of the encode kernel

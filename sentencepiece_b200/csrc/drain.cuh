@@ -49,7 +49,10 @@ __device__ __forceinline__ void drain_finish(const KBatch &B, uint32_t seg, uint
 // to its size compacts it.
 __device__ __forceinline__ void lane_drain(const KBatch &B, uint32_t sent, bool have, uint32_t lane) {
   if (!B.seg_done) return;
-  __threadfence();  // release: this group's results before the counters
+  // release: this group's results (stored by all 32 lanes) before the counters.  The warp barrier orders the lanes'
+  // stores before the leaders' RELEASE atomics below; a __threadfence() here would also invalidate the SM's L1
+  // (MEMBAR.SC + CCTL.IVALL) once per group -- see lane_wait_input.
+  __syncwarp();
   const uint32_t seg = have ? sent >> B.seg_shift : 0xFFFFFFFFu;
   const uint32_t peers = __match_any_sync(0xFFFFFFFFu, seg);
   const uint32_t leader = static_cast<uint32_t>(__ffs(peers)) - 1u;
@@ -58,7 +61,9 @@ __device__ __forceinline__ void lane_drain(const KBatch &B, uint32_t sent, bool 
     const uint32_t cnt = static_cast<uint32_t>(__popc(peers));
     const uint32_t seg_lo = seg << B.seg_shift;
     const uint32_t seg_n = min(B.n - seg_lo, 1u << B.seg_shift);
-    completes = atomicAdd(B.seg_done + seg, cnt) + cnt == seg_n;
+    uint32_t before;
+    asm volatile("atom.add.release.gpu.global.u32 %0, [%1], %2;" : "=r"(before) : "l"(B.seg_done + seg), "r"(cnt) : "memory");
+    completes = before + cnt == seg_n;
   }
   const uint32_t done = __ballot_sync(0xFFFFFFFFu, completes);
   if (!done) return;  // the usual case

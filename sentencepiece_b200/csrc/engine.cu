@@ -145,6 +145,10 @@ struct spm_engine {
   DevBuf<uint16_t> d_word_safe;
   DevBuf<uint4> d_node4;
   DevBuf<uint32_t> d_word_fast;
+  DevBuf<uint4> d_bpe_cache;
+  // SPM_B200_BPE_CACHE: log2 of the word-cache entries (64 bytes each), 0 = no cache.  Measured per 1M English
+  // sentences (profiles/README.md): none 6.58 ms, 2^16 6.57, 2^18 5.45, 2^20 4.66, 2^21 4.43, 2^22 4.16 ms (256 MB of HBM)
+  int bpe_cache_log2 = 22;
   int bpe_lane_version = 2;  // SPM_B200_BPE_LANE_V
   bool fast_words = true;  // SPM_B200_FASTWORDS
   int upload_word_safe();
@@ -154,6 +158,7 @@ struct spm_engine {
   int G = 1;  // 1: lane kernel (sentence per lane); 32: warp kernel; 4/8/16: tile kernel; 64: tile kernel, 32 lanes
   int threads = 1024;
   uint32_t ncap = 256;
+  uint32_t slab_discard = 1;  // SPM_B200_SLAB_DISCARD=0 turns it off (KBatch::slab_discard)
   uint32_t slab_l2 = 0;    // SPM_B200_SLAB_L2: L2 eviction priority of the slab accesses (KBatch::slab_l2)
   uint32_t lane_cap = 512;  // normalized-byte capacity per sentence of the lane kernel's slabs
   int ctas_per_sm = 1;
@@ -228,7 +233,8 @@ struct spm_engine {
         return g;
       g.version = bpe_lane_version == 2 ? 2 : 1;
       const size_t per_warp = g.version == 2 ? kBpeLane2WarpBytes : kBpeLaneWarpBytes;
-      const int warps = static_cast<int>(std::min<size_t>(std::min(threads, 768) / 32, avail / per_warp));
+      // (launch bounds: 704 threads for lane2 -- 22 warps is what the shared-memory arrays allow -- 768 for lane v1)
+      const int warps = static_cast<int>(std::min<size_t>(std::min(threads, g.version == 2 ? 704 : 768) / 32, avail / per_warp));
       if (warps < 4) return g;
       g.ok = true;
       g.threads = warps * 32;
@@ -652,6 +658,17 @@ int spm_engine::upload_word_safe() {
   CUDA_TRY(d_word_fast.upload(fastw));
   km.word_safe = d_word_safe.p;
   km.word_fast = d_word_fast.p;
+  // word cache of the BPE lane2 kernel: emptied whenever the tables change (the ids of a word are a function of the
+  // vocabulary and the live piece types)
+  km.bpe_cache = nullptr;
+  km.bpe_cache_mask = 0;
+  if (model.model_type == SPM_BPE && bpe_cache_log2 > 0) {
+    const size_t entries = size_t{1} << bpe_cache_log2;
+    CUDA_TRY(d_bpe_cache.ensure(entries * 4));
+    CUDA_TRY(cudaMemset(d_bpe_cache.p, 0, entries * 64));
+    km.bpe_cache = d_bpe_cache.p;
+    km.bpe_cache_mask = static_cast<uint32_t>(entries - 1);
+  }
   {
     std::vector<uint4> n4(trie.link.size());
     for (size_t u = 0; u < trie.link.size(); ++u) n4[u] = make_uint4(trie.link[u], trie.cmask[u], trie.val[u], safe[u]);
@@ -881,7 +898,7 @@ int spm_engine::run_device(const uint8_t *d_bytes_base, const uint64_t *d_offs, 
     CUDA_TRY(cudaMemsetAsync(d_ctrl32.p, 0, 16 * sizeof(uint32_t), st));
     CUDA_TRY(cudaMemsetAsync(d_ctrl64.p, 0, 4 * sizeof(unsigned long long), st));
     KBatch B{};
-    B.slab_l2 = slab_l2;
+    B.slab_l2 = slab_l2; B.slab_discard = slab_discard;
     B.bytes = d_bytes_base;
     B.offsets = d_offs;
     B.n = n32;
@@ -957,6 +974,11 @@ int spm_engine::run_device(const uint8_t *d_bytes_base, const uint64_t *d_offs, 
         fprintf(stderr, "[kstats] groups %llu: warp trips/group %.1f, lane trips/sentence %.1f (lane utilisation of K2 %.3f), starts/sentence "
                 "%.1f (whole words %.1f), normalized bytes/sentence %.1f\n", ks[12], double(ks[8]) / ks[12], double(ks[9]) / n,
                 double(ks[9]) / (32.0 * ks[8]), double(ks[10]) / n, double(ks[11]) / n, double(ks[13]) / n);
+      if (ks[4]) {
+        const double w = 1e-6 / (static_cast<double>(grid) * geom.tiles);
+        fprintf(stderr, "[kstats] M cycles per warp (lane 0): group loop %.2f = K1 %.2f, K2 %.2f, K4 %.2f, rest %.2f\n", ks[4] * w,
+                ks[5] * w, ks[6] * w, ks[7] * w, (ks[4] - ks[5] - ks[6] - ks[7]) * w);
+      }
     }
     uint32_t n_def = h_ctrl32.p[0];
     const uint32_t *def_list = d_deferred.p;
@@ -1375,6 +1397,11 @@ int spm_engine::encode_host_fused(const char *bytes, const uint64_t *offsets, si
   uint32_t kSegShift = 10;
   if (const char *v = getenv("SPM_B200_SEG_SHIFT")) kSegShift = std::min<uint32_t>(kPieceShift, std::max(8, atoi(v)));  // experiment knob
   if (const char *v = getenv("SPM_B200_PIECE_SHIFT")) kPieceShift = std::min(20, std::max(10, atoi(v)));
+  // experiment knobs (profiles/README.md, "fused path: what the kernel loses against the device-resident one"): bit 0 no
+  // D2H copies while the kernel runs, bit 1 id_offsets to device memory + one copy at the end, bit 2 the whole input is
+  // staged before the launch, bit 3 input order instead of the segment-sorted one.  All give correct results.
+  int fx = 0;
+  if (const char *v = getenv("SPM_B200_FUSED_X")) fx = atoi(v);
   const size_t kPiece = size_t{1} << kPieceShift;
   const size_t P = (n + kPiece - 1) / kPiece;
   const size_t S = (n + (size_t{1} << kSegShift) - 1) >> kSegShift;
@@ -1396,9 +1423,9 @@ int spm_engine::encode_host_fused(const char *bytes, const uint64_t *offsets, si
   CUDA_TRY(d_sent_rel.ensure(n));
   CUDA_TRY(d_deferred.ensure(2 * n + 2));
   CUDA_TRY(d_ctrl32.ensure(16));
-  CUDA_TRY(d_ctrl64.ensure(8));
+  CUDA_TRY(d_ctrl64.ensure(16));
   CUDA_TRY(h_ctrl32.ensure(16));
-  CUDA_TRY(h_ctrl64.ensure(8));
+  CUDA_TRY(h_ctrl64.ensure(16));
   CUDA_TRY(d_seg_done.ensure(2 * S + 4));   // groups finished [S], copied flags [S], drained counter
   CUDA_TRY(d_seg_words.ensure(2 * S));
   CUDA_TRY(d_ids.ensure(h_ids.cap));
@@ -1437,18 +1464,19 @@ int spm_engine::encode_host_fused(const char *bytes, const uint64_t *offsets, si
     }
   });
   struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{feeder};
+  if (fx & 4) { feeder.join(); CUDA_TRY(cudaStreamSynchronize(s_h2d)); }
   // ---- one launch ----
   last_launches = 0;
   last_deferred = 0;
   CUDA_TRY(cudaStreamWaitEvent(st, ev_offs, 0));
   CUDA_TRY(cudaMemsetAsync(d_ctrl32.p, 0, 16 * sizeof(uint32_t), st));
-  CUDA_TRY(cudaMemsetAsync(d_ctrl64.p, 0, 8 * sizeof(unsigned long long), st));
+  CUDA_TRY(cudaMemsetAsync(d_ctrl64.p, 0, 16 * sizeof(unsigned long long), st));
   CUDA_TRY(cudaMemsetAsync(d_seg_done.p, 0, (2 * S + 4) * sizeof(uint32_t), st));
   CUDA_TRY(cudaMemsetAsync(d_seg_words.p, 0, 2 * S * sizeof(unsigned long long), st));
   KModel M = km;
   M.hot_link = M.hot_val = 0;
   KBatch B{};
-  B.slab_l2 = slab_l2;
+  B.slab_l2 = slab_l2; B.slab_discard = slab_discard;
   B.bytes = s_bytes.p - offsets[0];
   B.offsets = s_offsets.p;
   B.n = n32;
@@ -1474,6 +1502,7 @@ int spm_engine::encode_host_fused(const char *bytes, const uint64_t *offsets, si
     void *dp = nullptr;
     CUDA_TRY(cudaHostGetDevicePointer(&dp, h_id_offsets.p, 0));
     B.out_offsets = static_cast<unsigned long long *>(dp);
+    if (fx & 2) { CUDA_TRY(d_id_offsets.ensure(n + 1)); B.out_offsets = d_id_offsets.p; }
     CUDA_TRY(cudaHostGetDevicePointer(&dp, h_progress.p, 0));
     B.host_progress = static_cast<unsigned long long *>(dp);
   }
@@ -1491,8 +1520,12 @@ int spm_engine::encode_host_fused(const char *bytes, const uint64_t *offsets, si
   // the segment size.
   uint32_t sort_shift = kSegShift;
   if (const char *v = getenv("SPM_B200_SORT_SHIFT")) sort_shift = std::min<uint32_t>(kPieceShift, std::max<uint32_t>(kSegShift, atoi(v)));
-  { const int rc = build_order(s_offsets.p, n, st, &B.order, 1u << sort_shift); if (rc) return rc; }
-  if (!B.order) { set_error("fused path needs the segment order"); return SPM_ERR_ARG; }
+  const bool fused_sort = !(fx & 8);  // bit 3: input order (completion is counted per sentence: any order drains)
+  if (fused_sort) {
+    const int rc = build_order(s_offsets.p, n, st, &B.order, 1u << sort_shift);
+    if (rc) return rc;
+    if (!B.order) { set_error("fused path needs the segment order"); return SPM_ERR_ARG; }
+  }
   if (bpe && lg.version == 2) encode_bpe_lane2_kernel<<<grid, lane_threads, smem, st>>>(M, B, d_lane_slabs.p, lane_cap, d_bpe_long.p);
   else if (bpe) encode_bpe_lane_kernel<<<grid, lane_threads, smem, st>>>(M, B, d_lane_slabs.p, lane_cap);
   else if (lg.version == 2) encode_unigram_lane_kernel<<<grid, lane_threads, smem, st>>>(M, B, d_lane_slabs.p, lane_cap, lg.R);
@@ -1502,7 +1535,7 @@ int spm_engine::encode_host_fused(const char *bytes, const uint64_t *offsets, si
   CUDA_TRY(cudaEventRecord(ev[1], st));
   CUDA_TRY(cudaEventRecord(ev[2], st));
   CUDA_TRY(cudaMemcpyAsync(h_ctrl32.p, d_ctrl32.p, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-  if (trace) CUDA_TRY(cudaMemcpyAsync(h_ctrl64.p, d_ctrl64.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  if (trace) CUDA_TRY(cudaMemcpyAsync(h_ctrl64.p, d_ctrl64.p, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   if (trace) fprintf(stderr, "[trace] fused kernel launched at %.3f ms\n", now_ms());
   // the offsets are checked while the GPU works (a decreasing pair only makes the kernels defer that sentence: the
   // lengths are taken as unsigned); a bad batch is reported after the launch has drained
@@ -1517,17 +1550,26 @@ int spm_engine::encode_host_fused(const char *bytes, const uint64_t *offsets, si
     if (q != cudaSuccess && q != cudaErrorNotReady) CUDA_TRY(q);
     const unsigned long long pr = *reinterpret_cast<volatile unsigned long long *>(h_progress.p);
     if (pr > seen && pr <= h_ids.cap) seen = pr;
-    if (seen - copied >= min_copy) {
+    if (!(fx & 1) && seen - copied >= min_copy) {
       CUDA_TRY(cudaMemcpyAsync(h_ids.p + copied, d_ids.p + copied, (seen - copied) * sizeof(int32_t), cudaMemcpyDeviceToHost, s_d2h));
       copied = seen;
     }
     if (q == cudaSuccess) break;
   }
   CUDA_TRY(cudaStreamSynchronize(st));
-  feeder.join();
+  if (feeder.joinable()) feeder.join();
+  if (fx & 2) CUDA_TRY(cudaMemcpy(h_id_offsets.p, d_id_offsets.p, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost));
   if (trace) fprintf(stderr, "[trace] fused kernel done at %.3f ms; warp-cycles: input wait %.1f M, compaction %.1f M (look-back %.1f M), "
                      "%llu groups on %d warps\n", now_ms(), h_ctrl64.p[4] * 1e-6, h_ctrl64.p[5] * 1e-6, h_ctrl64.p[6] * 1e-6,
                      static_cast<unsigned long long>(h_ctrl64.p[7]), grid * (lane_threads / 32));
+  if (trace) {
+    float km = 0.f;
+    cudaEventElapsedTime(&km, ev[0], ev[1]);
+    const double w = 1e-6 / (grid * (lane_threads / 32));  // M cycles per warp
+    fprintf(stderr, "[trace] kernel %.3f ms on the device; M cycles per warp (lane 0): group loop %.2f = K1 + input wait %.2f, K2 %.2f, "
+                    "K4 %.2f, drain %.2f\n", km, h_ctrl64.p[8] * w, h_ctrl64.p[9] * w, h_ctrl64.p[10] * w, h_ctrl64.p[11] * w,
+            (h_ctrl64.p[8] - h_ctrl64.p[9] - h_ctrl64.p[10] - h_ctrl64.p[11]) * w);
+  }
   if (bad) { cudaDeviceSynchronize(); set_error("offsets must be non-decreasing"); return SPM_ERR_ARG; }
   if (feed_rc) { cudaDeviceSynchronize(); set_error("host-to-device copy of a streamed batch failed"); return SPM_ERR_CUDA; }
   if (h_ctrl32.p[1] & 2u) { set_error("encode failed: the host-to-device copy of a streamed batch made no progress for 3 s"); return SPM_ERR_CUDA; }
@@ -1838,7 +1880,7 @@ int spm_engine::run_nbest(const char *bytes, const uint64_t *offsets, size_t n, 
     CUDA_TRY(cudaMemsetAsync(d_ctrl32.p, 0, 16 * sizeof(uint32_t), st));
     CUDA_TRY(cudaMemsetAsync(d_ctrl64.p, 0, 4 * sizeof(unsigned long long), st));
     KBatch B{};
-    B.slab_l2 = slab_l2;
+    B.slab_l2 = slab_l2; B.slab_discard = slab_discard;
     B.bytes = d_bytes.p - base;
     B.offsets = d_offsets.p;
     B.n = static_cast<uint32_t>(n);
@@ -1943,7 +1985,7 @@ int spm_engine::run_lattice(const char *bytes, const uint64_t *offsets, size_t n
       CUDA_TRY(cudaMemsetAsync(d_ctrl32.p, 0, 16 * sizeof(uint32_t), st));
       CUDA_TRY(cudaMemsetAsync(d_ctrl64.p, 0, 4 * sizeof(unsigned long long), st));
       KBatch B{};
-      B.slab_l2 = slab_l2;
+      B.slab_l2 = slab_l2; B.slab_discard = slab_discard;
       B.bytes = d_bytes.p - base;
       B.offsets = d_offsets.p;
       B.n = static_cast<uint32_t>(m);
@@ -2106,6 +2148,8 @@ static int create_common(spm_engine *e, int device, spm_engine **out) {
   if (const char *v = getenv("SPM_B200_FUSED")) e->fused_host_path = atoi(v) != 0;
   if (const char *v = getenv("SPM_B200_FASTWORDS")) e->force_fast_words = atoi(v) != 0 ? 1 : 0;
   if (const char *v = getenv("SPM_B200_KSTATS")) e->kstats = atoi(v) != 0;
+  if (const char *v = getenv("SPM_B200_BPE_CACHE")) e->bpe_cache_log2 = std::min(24, std::max(0, atoi(v)));
+  if (const char *v = getenv("SPM_B200_SLAB_DISCARD")) e->slab_discard = static_cast<uint32_t>(atoi(v));
   if (const char *v = getenv("SPM_B200_SLAB_L2")) e->slab_l2 = static_cast<uint32_t>(atoi(v));
   if (const char *v = getenv("SPM_B200_LANE_CAP")) e->lane_cap = std::min(1020, std::max(64, atoi(v))) & ~3;
   if (const char *v = getenv("SPM_B200_BPE_LANE_V")) e->bpe_lane_version = atoi(v);
@@ -2167,7 +2211,7 @@ void spm_engine_destroy(spm_engine *e) {
   if (e->stream) cudaStreamSynchronize(e->stream);
   e->d_link.release(); e->d_val.release(); e->d_user_link.release(); e->d_cm_units.release(); e->d_cm_lead.release();
   e->d_cm_pair.release(); e->d_id.release(); e->d_cm_solo.release(); e->d_byte_to_id.release(); e->d_cm_targets.release();
-  e->d_types.release(); e->d_scores.release(); e->d_word_safe.release(); e->d_node4.release(); e->d_word_fast.release(); e->d_kstats.release(); e->d_sample.release(); e->d_bytes.release(); e->d_tmp_norm.release(); e->d_norm.release();
+  e->d_types.release(); e->d_scores.release(); e->d_word_safe.release(); e->d_node4.release(); e->d_word_fast.release(); e->d_bpe_cache.release(); e->d_kstats.release(); e->d_sample.release(); e->d_bytes.release(); e->d_tmp_norm.release(); e->d_norm.release();
   e->d_long_scratch.release(); e->d_offsets.release(); e->d_tmp_ids.release(); e->d_ids.release();
   e->d_tmp_tok_end.release(); e->d_tok_end.release(); e->d_tmp_n2o.release(); e->d_n2o.release();
   e->d_sent_count.release(); e->d_norm_len.release(); e->d_deferred.release(); e->d_deferred2.release(); e->d_long_list.release();
@@ -2216,6 +2260,19 @@ int spm_engine_set_types(spm_engine *e, const uint8_t *types) {
   }
   e->model.types.assign(types, types + e->model.vocab_size());
   return e->upload_types();
+}
+
+int spm_engine_cache_reset(spm_engine *e) {
+  if (!e) return SPM_ERR_ARG;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (e->km.bpe_cache_mask) {
+    if (cudaSetDevice(e->device) != cudaSuccess ||
+        cudaMemset(e->d_bpe_cache.p, 0, (static_cast<size_t>(e->km.bpe_cache_mask) + 1) * 64) != cudaSuccess) {
+      e->set_error("spm_engine_cache_reset: cudaMemset failed");
+      return SPM_ERR_CUDA;
+    }
+  }
+  return SPM_OK;
 }
 
 static void finish_timing(spm_engine *e);

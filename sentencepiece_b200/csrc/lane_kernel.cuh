@@ -94,7 +94,10 @@ __device__ __forceinline__ void lane_wait_input(const KBatch &B, uint32_t first,
       }
       if (B.kstats) atomicAdd(B.kstats, static_cast<unsigned long long>(clock64() - t0));
     }
-    __threadfence();
+    // No fence here: __threadfence() is MEMBAR.SC + CCTL.IVALL on sm_100, and wiping the SM's L1 twice per group made
+    // the whole kernel 1.4x slower on the mixed-script corpus (profiles/README.md).  The input loads below are issued
+    // after this load has returned (the loop's exit depends on it), and they cannot hit a stale L1 line: a line of
+    // the input is first touched by a sentence of the piece it arrived with (copies are cut at 128-byte lines).
   }
   __syncwarp();
 }
@@ -129,6 +132,21 @@ __device__ __forceinline__ uint32_t slab_ld(const uint32_t *p, unsigned long lon
 }
 __device__ __forceinline__ void slab_st(uint32_t *p, uint32_t v, unsigned long long pol) {
   asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" :: "l"(p), "r"(v), "l"(pol) : "memory");
+}
+// End of a group: the rows of the warp's slab that the group used are dead.  Without a hint L2 keeps them as dirty
+// lines: they are written back to HBM when they are finally evicted (traffic for nothing) and, until then, they take
+// the place of the rows that are still live in other warps.  discard.L2 drops a line without write-back.  Warp-
+// collective; row r of a slab is one 128-byte line (32 lanes x 4 bytes).  The barriers order the group's last reads
+// before the discards and the discards before the next group's first writes (other lanes' words of the same line).
+__device__ __forceinline__ void slab_discard(const LaneCtx &c, uint32_t lane, uint32_t text_rows, uint32_t log_rows) {
+  __syncwarp();
+  const uint8_t *tb = reinterpret_cast<const uint8_t *>(c.text_w - lane);
+  for (uint32_t r = lane; r < text_rows; r += 32)
+    asm volatile("discard.global.L2 [%0], 128;" :: "l"(tb + static_cast<size_t>(r) * 128) : "memory");
+  const uint8_t *lb = reinterpret_cast<const uint8_t *>(c.log - lane);
+  for (uint32_t r = lane; r < log_rows; r += 32)
+    asm volatile("discard.global.L2 [%0], 128;" :: "l"(lb + static_cast<size_t>(r) * 128) : "memory");
+  __syncwarp();
 }
 
 // Sequential byte stream over a lane's input: 16-byte aligned chunks (next chunk prefetched)
@@ -483,6 +501,7 @@ __device__ __forceinline__ void lane_finish(const KModel &M, const KBatch &B, co
       }
     }
   }
+  if (B.slab_discard) slab_discard(c, lane, (__reduce_max_sync(0xFFFFFFFFu, n) >> 2) + 4u, max_log);
 }
 
 // shared memory per warp: ring of R slots, each {score f32, back-pointer u32, position tag u16} x 32 lanes
@@ -539,6 +558,8 @@ __global__ void __launch_bounds__(1024, 1) encode_unigram_lane_kernel(const KMod
     if (lane == 0) first = atomicAdd(B.work_counter, 32u);
     first = __shfl_sync(0xFFFFFFFFu, first, 0);
     if (first >= B.n) break;
+    const bool tst = B.kstats != nullptr;  // trace / kstats mode: phase clocks (lane 0)
+    const uint32_t t_g0 = tst ? static_cast<uint32_t>(clock64()) : 0u;
     lane_wait_input(B, first, lane);
     const bool have = first + lane < B.n;
     const uint32_t sent = have && B.order ? B.order[first + lane] : first + lane;
@@ -561,6 +582,7 @@ __global__ void __launch_bounds__(1024, 1) encode_unigram_lane_kernel(const KMod
       }
     }
     __syncwarp();
+    const uint32_t t_g1 = tst ? static_cast<uint32_t>(clock64()) : 0u;
     // ---------------- K2: flat state machine, one trie transition per trip ----------------
     // text window: words w0..w3 = bytes [4*aw, 4*aw+16), aw = s >> 2; `cur` streams the bytes
     // from the walk position k (low byte first).  ss = ring slot of s, times 32.
@@ -751,9 +773,16 @@ __global__ void __launch_bounds__(1024, 1) encode_unigram_lane_kernel(const KMod
         atomicAdd(B.kstats + 11, ull(st_fast)); atomicAdd(B.kstats + 12, ull(1)); atomicAdd(B.kstats + 13, ull(nb));
       }
     }
+    const uint32_t t_g2 = tst ? static_cast<uint32_t>(clock64()) : 0u;
     lane_finish(M, B, c, n, nlog, lane, have, defer, sent, bf);  // K4
+    const uint32_t t_g3 = tst ? static_cast<uint32_t>(clock64()) : 0u;
     lane_drain(B, sent, have, lane);  // K6 (fused host path only)
     __syncwarp();
+    if (tst && lane == 0) {
+      typedef unsigned long long ull;
+      atomicAdd(B.kstats + 4, ull(static_cast<uint32_t>(clock64()) - t_g0)); atomicAdd(B.kstats + 5, ull(t_g1 - t_g0));
+      atomicAdd(B.kstats + 6, ull(t_g2 - t_g1)); atomicAdd(B.kstats + 7, ull(t_g3 - t_g2));
+    }
   }
 }
 
@@ -797,6 +826,8 @@ __global__ void __launch_bounds__(1024, 1) encode_unigram_lane_plain_kernel(cons
     if (lane == 0) first = atomicAdd(B.work_counter, 32u);
     first = __shfl_sync(0xFFFFFFFFu, first, 0);
     if (first >= B.n) break;
+    const bool tst = B.kstats != nullptr;  // trace / kstats mode: phase clocks (lane 0)
+    const uint32_t t_g0 = tst ? static_cast<uint32_t>(clock64()) : 0u;
     lane_wait_input(B, first, lane);
     const bool have = first + lane < B.n;
     const uint32_t sent = have && B.order ? B.order[first + lane] : first + lane;
@@ -819,6 +850,7 @@ __global__ void __launch_bounds__(1024, 1) encode_unigram_lane_plain_kernel(cons
       }
     }
     __syncwarp();
+    const uint32_t t_g1 = tst ? static_cast<uint32_t>(clock64()) : 0u;
     // ---------------- K2: flat state machine, one trie transition per trip ----------------
     // text window: words w0..w3 = bytes [4*aw, 4*aw+16), aw = s >> 2; `cur` streams the bytes
     // from the walk position k (low byte first).
@@ -948,9 +980,16 @@ __global__ void __launch_bounds__(1024, 1) encode_unigram_lane_plain_kernel(cons
         }
       }
     }
+    const uint32_t t_g2 = tst ? static_cast<uint32_t>(clock64()) : 0u;
     lane_finish(M, B, c, n, nlog, lane, have, defer, sent, bf);  // K4
+    const uint32_t t_g3 = tst ? static_cast<uint32_t>(clock64()) : 0u;
     lane_drain(B, sent, have, lane);  // K6 (fused host path only)
     __syncwarp();
+    if (tst && lane == 0) {
+      typedef unsigned long long ull;
+      atomicAdd(B.kstats + 4, ull(static_cast<uint32_t>(clock64()) - t_g0)); atomicAdd(B.kstats + 5, ull(t_g1 - t_g0));
+      atomicAdd(B.kstats + 6, ull(t_g2 - t_g1)); atomicAdd(B.kstats + 7, ull(t_g3 - t_g2));
+    }
   }
 }
 

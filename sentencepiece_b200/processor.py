@@ -54,6 +54,10 @@ class Engine:
         t = np.ascontiguousarray(types, dtype=np.uint8)
         self._check(self._lib.spm_engine_set_types(self._h, t.ctypes.data))
 
+    def cache_reset(self):
+        """empties the engine's memo tables (the BPE word cache); results never depend on them"""
+        self._check(self._lib.spm_engine_cache_reset(self._h))
+
     def encode_packed(self, buf, offs, copy=True):
         """Batch encode of a packed host buffer -> (ids int32[], id_offsets uint64[n+1])."""
         n = len(offs) - 1

@@ -103,14 +103,39 @@ def test_set_vocabulary_live_types(model, corpus_gen):
     rng = np.random.default_rng(11)
     keep = [p for p in om.proto["pieces"] if rng.random() < 0.5]
     t = om.vocabulary_types(keep)
+    buf, offs = corpus_gen.fill("en", 4003, 3000)
+    # first with the full vocabulary (fills the BPE word cache, which must not survive the change of types)
+    assert_same(*eng.encode_packed(buf, offs), *om.encode_batch(buf, offs), "full vocabulary")
     om.set_types(t)
     eng.set_types(t)
-    buf, offs = corpus_gen.fill("en", 4003, 3000)
     assert_same(*eng.encode_packed(buf, offs), *om.encode_batch(buf, offs), "restricted vocabulary")
     om.set_types(om.types)
     eng.set_types(om.types)
     assert_same(*eng.encode_packed(buf, offs), *om.encode_batch(buf, offs), "reset vocabulary")
     eng.close()
+
+
+@pytest.mark.parametrize("model,kind", [("bpe32k", "en"), ("mix_bpe4k", "mixed")])
+def test_bpe_word_cache_is_transparent(model, kind, corpus_gen, monkeypatch):
+    """the BPE lane kernel's word cache (bpe_lane2_kernel.cuh) only ever returns what the merge loop would: cold cache,
+    warm cache (second call, other sentences with the same words), a tiny table (every slot contended) and no cache
+    give the oracle's ids"""
+    from sentencepiece_b200 import Engine
+    mb = model_bytes(model)
+    om = oracle_py.OracleModel(mb)
+    b1, o1 = corpus_gen.fill(kind, 4101, 20000)
+    b2, o2 = corpus_gen.fill(kind, 4102, 20000)
+    want1, want2 = om.encode_batch(b1, o1), om.encode_batch(b2, o2)
+    for log2 in (None, 8, 0):
+        if log2 is None:
+            monkeypatch.delenv("SPM_B200_BPE_CACHE", raising=False)
+        else:
+            monkeypatch.setenv("SPM_B200_BPE_CACHE", str(log2))
+        eng = Engine(mb)
+        assert_same(*eng.encode_packed(b1, o1), *want1, f"cold cache (log2 {log2})")
+        assert_same(*eng.encode_packed(b2, o2), *want2, f"warm cache (log2 {log2})")
+        assert_same(*eng.encode_packed(b1, o1), *want1, f"warm cache, first batch again (log2 {log2})")
+        eng.close()
 
 
 @pytest.mark.parametrize("flags", [dict(add_dummy_prefix=False), dict(remove_extra_whitespaces=False),

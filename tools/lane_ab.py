@@ -4,7 +4,8 @@ usage: python tools/lane_ab.py [model:kind ...] [--n N] [--variants "FW=0;FW=1;B
 Each variant is a ';'-separated item of ','-separated KEY=VALUE knobs:
   FW whole-word shortcut (SPM_B200_FASTWORDS), S length ordering (SPM_B200_SORT),
   T threads per CTA, BV BPE lane kernel version (SPM_B200_BPE_LANE_V), L2 eviction priority of the slab
-  accesses (SPM_B200_SLAB_L2: 0 normal, 1 evict_last, 2 evict_first), CAP slab capacity per lane (SPM_B200_LANE_CAP).
+  CR=1 empties the BPE word cache before every launch, C log2 of its entries (SPM_B200_BPE_CACHE), D discard of dead slab
+  rows (SPM_B200_SLAB_DISCARD), G sort block of the device path (SPM_B200_SORT_SEG), accesses (SPM_B200_SLAB_L2: 0 normal, 1 evict_last, 2 evict_first), CAP slab capacity per lane (SPM_B200_LANE_CAP).
 """
 import argparse
 import os
@@ -19,7 +20,7 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 import corpus  # noqa: E402
 from sentencepiece_b200 import Engine  # noqa: E402
 
-ENV = {"FW": "SPM_B200_FASTWORDS", "L2": "SPM_B200_SLAB_L2", "CAP": "SPM_B200_LANE_CAP",
+ENV = {"FW": "SPM_B200_FASTWORDS", "L2": "SPM_B200_SLAB_L2", "D": "SPM_B200_SLAB_DISCARD", "C": "SPM_B200_BPE_CACHE", "G": "SPM_B200_SORT_SEG", "CAP": "SPM_B200_LANE_CAP",
        "BV": "SPM_B200_BPE_LANE_V", "S": "SPM_B200_SORT"}
 
 ap = argparse.ArgumentParser()
@@ -57,6 +58,8 @@ for wl in args.workloads:
                 eng.set_tuning(0, 0, int(knobs["T"]))
             ms = []
             for _ in range(args.reps):
+                if knobs.get("CR") == "1":
+                    eng.cache_reset()  # BPE: every launch starts with an empty word cache
                 tot = eng.encode_device(d_bytes.data_ptr(), d_offs.data_ptr(), n, total, d_ids.data_ptr(), cap,
                                         d_ido.data_ptr(), None)
                 info = eng.info()
