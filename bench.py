@@ -562,7 +562,8 @@ def run_encode_workload(args, workload, rank, world, local_rank, scaling, light=
         kernel_ms = statistics.mean(main_ms)
         achieved = alg_bytes / (kernel_ms / 1e3) / 1e9
         tr = load_traffic(workload, n)
-        kname = "encode_bpe_lane2_kernel" if "bpe" in model else "encode_unigram_lane_kernel"
+        kname = ("encode_bpe_lane2_kernel" if "bpe" in model else
+                 "encode_unigram_lane_plain_kernel" if kind == "mixed" else "encode_unigram_lane_kernel")
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": tr["traffic_bytes"] if tr else None, "traffic_source": tr["source"] if tr else None,
                     "kernel": kname, "kernel_ms": kernel_ms, "launches_per_step": C,
