@@ -666,6 +666,7 @@ int spm_engine::upload_word_safe() {
     const size_t entries = size_t{1} << bpe_cache_log2;
     CUDA_TRY(d_bpe_cache.ensure(entries * 4));
     CUDA_TRY(cudaMemset(d_bpe_cache.p, 0, entries * 64));
+    CUDA_TRY(cudaDeviceSynchronize());
     km.bpe_cache = d_bpe_cache.p;
     km.bpe_cache_mask = static_cast<uint32_t>(entries - 1);
   }
@@ -2266,8 +2267,11 @@ int spm_engine_cache_reset(spm_engine *e) {
   if (!e) return SPM_ERR_ARG;
   std::lock_guard<std::mutex> lk(e->mu);
   if (e->km.bpe_cache_mask) {
+    // (the engine's streams do not synchronize with the legacy stream: the fill runs on the engine's own stream and is
+    // complete when the call returns, whatever stream the next batch uses)
     if (cudaSetDevice(e->device) != cudaSuccess ||
-        cudaMemset(e->d_bpe_cache.p, 0, (static_cast<size_t>(e->km.bpe_cache_mask) + 1) * 64) != cudaSuccess) {
+        cudaMemsetAsync(e->d_bpe_cache.p, 0, (static_cast<size_t>(e->km.bpe_cache_mask) + 1) * 64, e->stream) != cudaSuccess ||
+        cudaStreamSynchronize(e->stream) != cudaSuccess) {
       e->set_error("spm_engine_cache_reset: cudaMemset failed");
       return SPM_ERR_CUDA;
     }

@@ -1,4 +1,5 @@
-"""one-off: host-path traces (SPM_B200_TRACE=1) of the fused path for the bench corpora"""
+"""Host-path traces of the fused path (SPM_B200_TRACE=1: timeline + per-phase cycles per warp) for the bench corpora.
+usage: python tools/trace_e2e.py [model:kind ...]   (env: SPM_B200_FUSED_X experiment bits, T threads per CTA)"""
 import os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
