@@ -170,6 +170,29 @@ __device__ __forceinline__ uint32_t charsmap_longest(const KModel &M, const uint
   return longest;
 }
 
+// The same walk with the first `have` bytes taken from a register window (the lane kernels' ByteStream holds the next
+// 5..8 input bytes): no global byte load in front of every trie step for the usual 2..4-byte keys.
+__device__ __forceinline__ uint32_t charsmap_longest_win(const KModel &M, unsigned long long win, uint32_t have,
+                                                         const uint8_t *p, uint32_t len, uint32_t *value) {
+  uint32_t longest = 0;
+  uint32_t node = 0;
+  uint32_t unit = __ldg(M.cm_units);
+  node ^= da_offset(unit);
+  for (uint32_t i = 0; i < len; ++i) {
+    const uint32_t c = i < have ? static_cast<uint32_t>(win >> (8u * i)) & 0xFFu : static_cast<uint32_t>(p[i]);
+    node ^= c;
+    if (node >= M.cm_nunits) break;
+    unit = __ldg(M.cm_units + node);
+    if (da_label(unit) != c) break;
+    node ^= da_offset(unit);
+    if ((unit >> 8) & 1u) {
+      longest = i + 1;
+      *value = __ldg(M.cm_units + node) & 0x7FFFFFFFu;
+    }
+  }
+  return longest;
+}
+
 // PrefixMatcher::PrefixMatch over the user-defined-symbol trie (normalizer.cc:324-346):
 // longest user symbol that is a prefix of p, 0 if none.
 __device__ __forceinline__ uint32_t user_longest(const KModel &M, const uint8_t *p, uint32_t len) {

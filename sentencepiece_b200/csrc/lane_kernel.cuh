@@ -292,13 +292,13 @@ __device__ __forceinline__ uint32_t lane_normalize(const KModel &M, const uint8_
             const uint32_t c2 = S.peek(1);
             cont = (c.s_pair[(b * 256u + c2) >> 5] >> (c2 & 31u)) & 1u;
           }
-          if (cont) longest = charsmap_longest(M, in + pos, rem, &value);
+          if (cont) longest = charsmap_longest_win(M, S.win, S.have, in + pos, rem, &value);
           else {
             const int32_t so = c.s_solo[b];
             if (so >= 0) { longest = 1; value = static_cast<uint32_t>(so); }
           }
         } else {
-          longest = charsmap_longest(M, in + pos, rem, &value);
+          longest = charsmap_longest_win(M, S.win, S.have, in + pos, rem, &value);
         }
       }
       if (longest) {
